@@ -1,0 +1,48 @@
+"""Generates tests/golden/* from the reference's own media and from the oracle.  Run in the build
+container (needs /root/reference); the outputs are committed so nothing reads /root/reference at test time.
+
+  book2_motion_blur_rgb8.npz : the 8-bit RGB raster of /root/reference/media/book2_motion_blur.png
+                               (the reference's own render of random_scene, 384x216) — decoded, not re-rendered.
+  c1_oracle_digest.json      : sha256 of the oracle's float64 framebuffer for config C1 in both math modes,
+                               plus its deterministic counters (primary rays / segments).
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+from PIL import Image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    png = np.asarray(Image.open("/root/reference/media/book2_motion_blur.png").convert("RGB"))
+    assert png.shape == (216, 384, 3)
+    np.savez_compressed(os.path.join(GOLD, "book2_motion_blur_rgb8.npz"), rgb8=png)
+
+    world = O.random_scene()
+    cam = O.book_camera()
+    digest = {"config": "random_scene seed 0xFACADE, 384x216, 100 spp, depth 50, gamma float32(2.2)"}
+    for math in ("libm", "det"):
+        cnt = {}
+        img = O.render(216, 384, 100, cam, world, math=math, counters=cnt)
+        q = O.quantise_rgb8(img)
+        digest[math] = {
+            "f64_sha256": hashlib.sha256(img.tobytes()).hexdigest(),
+            "rgb8_sha256": hashlib.sha256(q.tobytes()).hexdigest(),
+            "rgb8_equals_reference_png": bool(np.array_equal(q, png)),
+            "counters": cnt,
+        }
+    with open(os.path.join(GOLD, "c1_oracle_digest.json"), "w") as f:
+        json.dump(digest, f, indent=1)
+    print(json.dumps(digest, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,340 @@
+"""Host-side mirror of the reference's Nim API over the C ABI (ctypes).
+
+Reference interface mirrored here (paths under /root/reference/trace_of_radiance/):
+  render(canvas, cam, world, max_depth)            render.nim:49
+  camera(lookFrom, lookAt, view_up, vfov, ...)     physics/cameras.nim:24-45
+  Scene.add / Scene.list() -> HittableList         physics/hittables/hittables_lists.nim:15-46
+  sphere / movingSphere                            physics/hittables/spheres.nim:20-26, moving_spheres.nim:22-37
+  lambertian / metal / dielectric                  physics/materials.nim:21,35,52
+  newCanvas / Canvas                               primitives/canvas.nim:21-45
+  exportToPPM                                      io/ppm.nim:14-27
+  random_scene                                     scenes.nim:13-50
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libtor_b200.so"
+
+# tor_hittable (include/tor_b200.h), 112 bytes
+HITTABLE_DTYPE = np.dtype(
+    [
+        ("kind", "<u4"),
+        ("mat_kind", "<u4"),
+        ("center0", "<f8", (3,)),
+        ("center1", "<f8", (3,)),
+        ("time0", "<f8"),
+        ("time1", "<f8"),
+        ("radius", "<f8"),
+        ("albedo", "<f8", (3,)),
+        ("fuzz_or_ior", "<f8"),
+    ],
+    align=False,
+)
+assert HITTABLE_DTYPE.itemsize == 112
+
+TOR_SPHERE, TOR_MOVING_SPHERE = 0, 1
+TOR_LAMBERTIAN, TOR_METAL, TOR_DIELECTRIC = 0, 1, 2
+TOR_FLAG_COUNT_SEGMENTS = 0x100
+
+EXPORTED_SYMBOLS = [
+    "tor_abi_version", "tor_ctx_create", "tor_ctx_destroy", "tor_last_error", "tor_render", "tor_render_rows",
+    "tor_scene_upload", "tor_render_device_async", "tor_sync", "tor_get_counters", "tor_last_kernel_ms",
+    "tor_launch_count", "tor_camera_make", "tor_random_scene", "tor_export_ppm", "tor_quantise_rgb8",
+]
+
+
+class TorError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"tor_b200 error {code}: {msg}")
+        self.code = code
+
+
+class _CCamera(C.Structure):  # tor_camera == cameras.nim:15-22
+    _fields_ = [(n, C.c_double * 3) for n in ("origin", "lower_left_corner", "horizontal", "vertical", "u", "v", "w")] + [
+        ("lens_radius", C.c_double), ("shutter_open", C.c_double), ("shutter_close", C.c_double)]
+
+
+class _CCanvas(C.Structure):  # tor_canvas == canvas.nim:21-28
+    _fields_ = [("pixels", C.POINTER(C.c_double)), ("nrows", C.c_int32), ("ncols", C.c_int32),
+                ("samples_per_pixel", C.c_int32), ("gamma_correction", C.c_float)]
+
+
+assert C.sizeof(_CCamera) == 192 and C.sizeof(_CCanvas) == 24
+
+_lib = None
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", _LIB_NAME)
+
+
+def load_library():
+    """Load libtor_b200.so.  Raises (never falls back) when the CUDA library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `make -C trace_of_radiance_b200/csrc` "
+                          "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.tor_abi_version.restype = C.c_int
+    L.tor_ctx_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.tor_ctx_destroy.argtypes = [vp]
+    L.tor_ctx_destroy.restype = None
+    L.tor_last_error.argtypes = [vp]
+    L.tor_last_error.restype = C.c_char_p
+    L.tor_render.argtypes = [vp, C.POINTER(_CCanvas), C.POINTER(_CCamera), vp, C.c_int64, C.c_int64, C.c_int64, C.c_uint32]
+    L.tor_render_rows.argtypes = L.tor_render.argtypes + [C.c_int32, C.c_int32, C.c_int32]
+    L.tor_scene_upload.argtypes = [vp, C.POINTER(_CCamera), vp, C.c_int64, C.c_int64]
+    L.tor_render_device_async.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int64, C.c_uint32,
+                                          C.c_int32, C.c_int32, C.c_int32, vp]
+    L.tor_sync.argtypes = [vp]
+    L.tor_get_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.tor_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.tor_launch_count.argtypes = [vp]
+    L.tor_launch_count.restype = C.c_int64
+    L.tor_camera_make.argtypes = [C.POINTER(_CCamera)] + [C.POINTER(C.c_double)] * 3 + [C.c_double] * 6
+    L.tor_camera_make.restype = None
+    L.tor_random_scene.argtypes = [C.c_uint64, C.c_int32, vp, C.c_int64]
+    L.tor_random_scene.restype = C.c_int64
+    L.tor_export_ppm.argtypes = [C.POINTER(_CCanvas), C.c_char_p]
+    L.tor_quantise_rgb8.argtypes = [C.POINTER(_CCanvas), C.POINTER(C.c_uint8)]
+    _lib = L
+    return L
+
+
+# ------------------------------------------------------------------------------- materials
+def lambertian(albedo):
+    """materials.nim:21"""
+    return (TOR_LAMBERTIAN, tuple(float(a) for a in albedo), 0.0)
+
+
+def metal(albedo, fuzz):
+    """materials.nim:35-37 — fuzz is clamped to <= 1."""
+    fuzz = float(fuzz)
+    return (TOR_METAL, tuple(float(a) for a in albedo), fuzz if fuzz <= 1.0 else 1.0)
+
+
+def dielectric(refraction_index):
+    """materials.nim:52"""
+    return (TOR_DIELECTRIC, (0.0, 0.0, 0.0), float(refraction_index))
+
+
+# ------------------------------------------------------------------------------- hittables
+def sphere(center, radius, material):
+    """spheres.nim:20-26"""
+    h = np.zeros((), dtype=HITTABLE_DTYPE)
+    h["kind"] = TOR_SPHERE
+    h["mat_kind"], h["albedo"], h["fuzz_or_ior"] = material
+    h["center0"] = center
+    h["radius"] = radius
+    return h
+
+
+def movingSphere(center0, time0, center1, time1, radius, material):
+    """moving_spheres.nim:22-37"""
+    h = sphere(center0, radius, material)
+    h["kind"] = TOR_MOVING_SPHERE
+    h["center1"] = center1
+    h["time0"] = time0
+    h["time1"] = time1
+    return h
+
+
+class HittableList:
+    """hittables_lists.nim:20-24 — a non-owning (len, pointer) view; here a contiguous record array."""
+
+    def __init__(self, objects):
+        self.objects = np.ascontiguousarray(objects, dtype=HITTABLE_DTYPE)
+
+    def __len__(self):
+        return int(self.objects.shape[0])
+
+
+class Scene:
+    """hittables_lists.nim:15-46"""
+
+    def __init__(self, objects=None):
+        self._objs = [] if objects is None else [o for o in np.asarray(objects, dtype=HITTABLE_DTYPE)]
+
+    def add(self, h):
+        self._objs.append(np.asarray(h, dtype=HITTABLE_DTYPE))
+
+    def clear(self):
+        self._objs = []
+
+    def __len__(self):
+        return len(self._objs)
+
+    def list(self):
+        assert len(self._objs) > 0  # hittables_lists.nim:42
+        return HittableList(np.array(self._objs, dtype=HITTABLE_DTYPE))
+
+
+def random_scene(seed=0xFACADE, half=11):
+    """scenes.nim:13-50 with `worldRNG.seed(seed)` (trace_of_radiance.nim:34-36)."""
+    L = load_library()
+    n = L.tor_random_scene(seed, half, None, 0)
+    buf = np.zeros(n, dtype=HITTABLE_DTYPE)
+    L.tor_random_scene(seed, half, buf.ctypes.data, n)
+    return Scene(buf)
+
+
+# ---------------------------------------------------------------------------------- camera
+class Camera:
+    """cameras.nim:15-22 as 24 float64."""
+
+    def __init__(self, c=None):
+        self.c = c if c is not None else _CCamera()
+
+    def as_array(self):
+        return np.frombuffer(bytes(self.c), dtype=np.float64).copy()
+
+    @staticmethod
+    def from_array(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.size == 24
+        return Camera(_CCamera.from_buffer_copy(a.tobytes()))
+
+
+def camera(lookFrom, lookAt, view_up, vertical_field_of_view, aspect_ratio, aperture, focus_distance,
+           shutterOpen=0.0, shutterClose=0.0):
+    """cameras.nim:24-45"""
+    L = load_library()
+    v = [(C.c_double * 3)(*[float(x) for x in p]) for p in (lookFrom, lookAt, view_up)]
+    cam = _CCamera()
+    L.tor_camera_make(C.byref(cam), v[0], v[1], v[2], vertical_field_of_view, aspect_ratio, aperture, focus_distance,
+                      shutterOpen, shutterClose)
+    return Camera(cam)
+
+
+# ---------------------------------------------------------------------------------- canvas
+class Canvas:
+    """canvas.nim:21-28.  pixels: (nrows, ncols, 3) float64, row 0 = bottom of the image."""
+
+    def __init__(self, height, width, samples_per_pixel, gamma_correction):
+        self.nrows, self.ncols = int(height), int(width)
+        self.samples_per_pixel = int(samples_per_pixel)
+        self.gamma_correction = float(np.float32(gamma_correction))
+        self.pixels = np.zeros((self.nrows, self.ncols, 3), dtype=np.float64)
+
+    def _c(self):
+        return _CCanvas(self.pixels.ctypes.data_as(C.POINTER(C.c_double)), self.nrows, self.ncols,
+                        self.samples_per_pixel, self.gamma_correction)
+
+    def __getitem__(self, rc):  # canvas.nim:56-57
+        return self.pixels[rc[0], rc[1]]
+
+    def toRGB8(self):
+        """io/ppm.nim quantisation, PPM row order (top row first): (nrows, ncols, 3) uint8."""
+        out = np.zeros((self.nrows, self.ncols, 3), dtype=np.uint8)
+        c = self._c()
+        rc = load_library().tor_quantise_rgb8(C.byref(c), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        if rc:
+            raise TorError(rc, "tor_quantise_rgb8")
+        return out
+
+
+def newCanvas(height, width, samples_per_pixel, gamma_correction):
+    """canvas.nim:31-41"""
+    return Canvas(height, width, samples_per_pixel, gamma_correction)
+
+
+def exportToPPM(canvas, path):
+    """io/ppm.nim:14-27 (to a file path instead of a Nim File)."""
+    c = canvas._c()
+    rc = load_library().tor_export_ppm(C.byref(c), os.fsencode(path))
+    if rc:
+        raise TorError(rc, f"cannot write {path}")
+
+
+# --------------------------------------------------------------------------------- context
+class Context:
+    """tor_ctx: device buffers + streams for one calling thread."""
+
+    def __init__(self, devices=None):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.L.tor_ctx_create(arr, len(devices), C.byref(self.h))
+        else:
+            rc = self.L.tor_ctx_create(None, 0, C.byref(self.h))
+        if rc:
+            raise TorError(rc, (self.L.tor_last_error(None) or b"").decode())
+
+    def _check(self, rc):
+        if rc:
+            raise TorError(rc, (self.L.tor_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if self.h:
+            self.L.tor_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render(self, canvas, cam, world, max_depth, flags=0, rows=None):
+        c = canvas._c()
+        objs = world.objects
+        if rows is None:
+            self._check(self.L.tor_render(self.h, C.byref(c), C.byref(cam.c), objs.ctypes.data, len(objs),
+                                          objs.dtype.itemsize, max_depth, flags))
+        else:
+            rb, re, rs = rows
+            self._check(self.L.tor_render_rows(self.h, C.byref(c), C.byref(cam.c), objs.ctypes.data, len(objs),
+                                               objs.dtype.itemsize, max_depth, flags, rb, re, rs))
+
+    def render_raw(self, canvas, cam, objects_ptr, length, stride, max_depth, flags=0):
+        """Same call with an explicit (pointer, len, stride) — e.g. the 120-byte Nim variant encoding."""
+        c = canvas._c()
+        self._check(self.L.tor_render(self.h, C.byref(c), C.byref(cam.c), objects_ptr, length, stride, max_depth, flags))
+
+    def scene_upload(self, cam, world):
+        objs = world.objects
+        self._check(self.L.tor_scene_upload(self.h, C.byref(cam.c), objs.ctypes.data, len(objs), objs.dtype.itemsize))
+
+    def render_device_async(self, d_pixels_ptr, nrows, ncols, spp, gamma, max_depth, flags=0, rows=None, stream=None):
+        rb, re, rs = rows if rows is not None else (0, nrows, 1)
+        self._check(self.L.tor_render_device_async(self.h, d_pixels_ptr, nrows, ncols, spp, float(np.float32(gamma)),
+                                                   max_depth, flags, rb, re, rs, stream))
+
+    def sync(self):
+        self._check(self.L.tor_sync(self.h))
+
+    def counters(self):
+        out = (C.c_uint64 * 3)()
+        self._check(self.L.tor_get_counters(self.h, out))
+        return {"primary_rays": int(out[0]), "segments": int(out[1]), "sphere_tests": int(out[2])}
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._check(self.L.tor_last_kernel_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self):
+        return int(self.L.tor_launch_count(self.h))
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+def render(canvas, cam, world, max_depth, ctx=None):
+    """render.nim:49 — `canvas.render(cam, world.list(), max_depth)`.  Synchronous."""
+    (ctx or default_context()).render(canvas, cam, world, max_depth)

@@ -1,0 +1,396 @@
+// tor_api.cu — the C ABI of include/tor_b200.h over the sm_100a render kernel.
+//
+// Replaces `proc render*(canvas: var Canvas, cam: Camera, world: HittableList, max_depth: int)`
+// (trace_of_radiance/render.nim:49).  There is deliberately NO CPU path in this file: without a
+// CUDA device every compute entry point fails with TOR_ERR_NO_DEVICE / TOR_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/tor_b200.h"
+#include "tor_kernels.cuh"
+#include "tor_scene_pack.hpp"
+
+namespace {
+
+constexpr int kBlock = 256;
+
+struct DeviceState {
+  int dev = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  uint8_t* d_blob = nullptr;
+  size_t blob_cap = 0;
+  double* d_pixels = nullptr;
+  size_t pix_cap = 0;  // bytes
+  unsigned long long* d_work = nullptr;      // pixel queue head
+  unsigned long long* d_counters = nullptr;  // [0] primary rays, [1] segments
+  bool scene_current = false;
+  bool timed = false;
+};
+
+}  // namespace
+
+struct tor_ctx {
+  std::vector<DeviceState> devs;
+  std::string err;
+  tor::PackedScene scene;
+  tor_camera cam;
+  bool have_scene = false;
+  int64_t launches = 0;
+  uint64_t counters[3] = {0, 0, 0};
+  bool counters_pending = false;
+};
+
+namespace {
+
+thread_local std::string g_create_err;
+
+int fail(tor_ctx* ctx, int code, const std::string& msg) {
+  if (ctx)
+    ctx->err = msg;
+  else
+    g_create_err = msg;
+  return code;
+}
+
+#define TOR_CUDA(ctx, call)                                                                      \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(ctx, TOR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+using KernelFn = void (*)(const tor::RenderParams);
+
+struct LaunchPlan {
+  KernelFn fn;
+  int stage;
+  size_t smem;
+};
+
+LaunchPlan plan_for(const tor::SceneView& sv, int max_smem_optin) {
+  const size_t cand = (size_t)tor::kMaxCand * kBlock * sizeof(uint16_t);
+  // two CTAs per SM want <= ~113 KB each; a bigger scene simply runs one CTA per SM
+  if (sv.total_bytes + cand <= (size_t)max_smem_optin)
+    return LaunchPlan{tor::render_exact_kernel<kBlock, 2>, 2, sv.total_bytes + cand};
+  if (sv.hot_bytes + cand <= (size_t)max_smem_optin)
+    return LaunchPlan{tor::render_exact_kernel<kBlock, 1>, 1, sv.hot_bytes + cand};
+  return LaunchPlan{tor::render_exact_kernel<kBlock, 0>, 0, cand};
+}
+
+int ensure_capacity(tor_ctx* ctx, DeviceState& d, size_t blob_bytes, size_t pix_bytes) {
+  TOR_CUDA(ctx, cudaSetDevice(d.dev));
+  if (blob_bytes > d.blob_cap) {
+    if (d.d_blob) cudaFree(d.d_blob);
+    d.d_blob = nullptr;
+    d.blob_cap = 0;
+    TOR_CUDA(ctx, cudaMalloc(&d.d_blob, blob_bytes));
+    d.blob_cap = blob_bytes;
+    d.scene_current = false;
+  }
+  if (pix_bytes > d.pix_cap) {
+    if (d.d_pixels) cudaFree(d.d_pixels);
+    d.d_pixels = nullptr;
+    d.pix_cap = 0;
+    TOR_CUDA(ctx, cudaMalloc(&d.d_pixels, pix_bytes));
+    d.pix_cap = pix_bytes;
+  }
+  return TOR_OK;
+}
+
+int upload_scene_to(tor_ctx* ctx, DeviceState& d) {
+  if (d.scene_current) return TOR_OK;
+  int rc = ensure_capacity(ctx, d, ctx->scene.blob.size(), 0);
+  if (rc) return rc;
+  TOR_CUDA(ctx, cudaMemcpyAsync(d.d_blob, ctx->scene.blob.data(), ctx->scene.blob.size(), cudaMemcpyHostToDevice,
+                                d.stream));
+  // the blob vector may be rebuilt by the next tor_scene_upload: finish the copy before returning
+  TOR_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  d.scene_current = true;
+  return TOR_OK;
+}
+
+int set_scene(tor_ctx* ctx, const tor_camera* cam, const void* objects, int64_t len, int64_t stride) {
+  if (!cam) return fail(ctx, TOR_ERR_INVALID_ARG, "camera is NULL");
+  if (!objects || len <= 0)
+    return fail(ctx, TOR_ERR_INVALID_ARG, "empty HittableList (hittables_lists.nim:42 asserts len > 0)");
+  if (stride != TOR_STRIDE_FLAT && stride != TOR_STRIDE_NIM_VARIANT)
+    return fail(ctx, TOR_ERR_LAYOUT, "stride must be 112 (tor_hittable) or 120 (Nim HittableVariant)");
+  if (len > 65535) return fail(ctx, TOR_ERR_SCENE_TOO_LARGE, "more than 65535 objects");
+  std::string err;
+  if (!tor::pack_scene(objects, len, stride, cam->shutter_open, cam->shutter_close, &ctx->scene, &err)) {
+    ctx->have_scene = false;
+    return fail(ctx, TOR_ERR_INVALID_ARG, err);
+  }
+  ctx->cam = *cam;
+  ctx->have_scene = true;
+  for (DeviceState& d : ctx->devs) d.scene_current = false;
+  return TOR_OK;
+}
+
+int check_canvas_dims(tor_ctx* ctx, int32_t nrows, int32_t ncols, int32_t spp, int64_t max_depth, int32_t row_begin,
+                      int32_t row_end, int32_t row_step) {
+  if (nrows <= 0 || ncols <= 0) return fail(ctx, TOR_ERR_INVALID_ARG, "canvas has no pixels");
+  if (spp < 0) return fail(ctx, TOR_ERR_INVALID_ARG, "samples_per_pixel < 0");
+  if (max_depth < 0 || max_depth > 0x7fffffff) return fail(ctx, TOR_ERR_INVALID_ARG, "max_depth out of range");
+  if (row_step <= 0 || row_begin < 0 || row_end > nrows)
+    return fail(ctx, TOR_ERR_INVALID_ARG, "row range outside the canvas");
+  return TOR_OK;
+}
+
+// Enqueue one render of rows row_begin, row_begin+row_step, ... < row_end on device `d` into d_out.
+int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int32_t ncols, int32_t spp, float gamma,
+                int64_t max_depth, uint32_t flags, int32_t row_begin, int32_t row_end, int32_t row_step,
+                cudaStream_t stream, bool timed) {
+  const int32_t nsel = row_end > row_begin ? (row_end - row_begin + row_step - 1) / row_step : 0;
+  d.timed = false;
+  if (nsel == 0) return TOR_OK;
+  TOR_CUDA(ctx, cudaSetDevice(d.dev));
+
+  tor::RenderParams P;
+  memset(&P, 0, sizeof(P));
+  P.sv = ctx->scene.view;
+  P.blob = d.d_blob;
+  P.cam = ctx->cam;
+  P.pixels = d_out;
+  P.nrows = nrows;
+  P.ncols = ncols;
+  P.spp = spp;
+  P.max_depth = (int32_t)max_depth;
+  P.inv_spp = 1.0 / (double)spp;             // canvas.nim:49
+  P.inv_gamma = 1.0 / (double)gamma;         // canvas.nim:50 — float32 widened to float64
+  P.row_begin = row_begin;
+  P.row_step = row_step;
+  P.nsel_rows = nsel;
+  P.count_segments = (flags & TOR_FLAG_COUNT_SEGMENTS) ? 1u : 0u;
+  P.work_counter = d.d_work;
+  P.counters = d.d_counters;
+
+  LaunchPlan plan = plan_for(P.sv, d.max_smem_optin);
+  TOR_CUDA(ctx, cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+  int per_sm = 0;
+  TOR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, kBlock, plan.smem));
+  if (per_sm < 1) return fail(ctx, TOR_ERR_CUDA, "render kernel does not fit on an SM");
+  // persistent lanes: one grid that exactly fills the GPU; lanes pull pixels from d_work
+  unsigned long long total_px = (unsigned long long)nsel * (unsigned long long)ncols;
+  unsigned long long want = (total_px + kBlock - 1) / kBlock;
+  unsigned long long cap = (unsigned long long)d.sm_count * (unsigned long long)per_sm;
+  int grid = (int)(want < cap ? want : cap);
+
+  TOR_CUDA(ctx, cudaMemsetAsync(d.d_work, 0, sizeof(unsigned long long), stream));
+  if (timed) TOR_CUDA(ctx, cudaEventRecord(d.ev0, stream));
+  plan.fn<<<grid, kBlock, plan.smem, stream>>>(P);
+  TOR_CUDA(ctx, cudaGetLastError());
+  if (timed) {
+    TOR_CUDA(ctx, cudaEventRecord(d.ev1, stream));
+    d.timed = true;
+  }
+  ctx->launches += 1;
+  if (P.count_segments) ctx->counters_pending = true;
+  return TOR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tor_abi_version(void) { return TOR_B200_ABI_VERSION; }
+
+const char* tor_last_error(const tor_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int tor_ctx_create(const int* devices, int ndev, tor_ctx** out) {
+  if (!out) return fail(nullptr, TOR_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, TOR_ERR_NO_DEVICE,
+                std::string("no CUDA device (this library has no CPU path): ") + cudaGetErrorString(e));
+  std::vector<int> ids;
+  if (!devices || ndev <= 0) {
+    ids.push_back(0);
+  } else {
+    for (int i = 0; i < ndev; ++i) {
+      if (devices[i] < 0 || devices[i] >= count)
+        return fail(nullptr, TOR_ERR_INVALID_ARG, "device index out of range");
+      ids.push_back(devices[i]);
+    }
+  }
+  tor_ctx* ctx = new tor_ctx();
+  for (int id : ids) {
+    DeviceState d;
+    d.dev = id;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(id)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, id)) != cudaSuccess) {
+      g_create_err = std::string("cudaSetDevice/GetDeviceProperties: ") + cudaGetErrorString(e);
+      tor_ctx_destroy(ctx);
+      return TOR_ERR_CUDA;
+    }
+    if (prop.major < 10) {
+      g_create_err = "device is not sm_100-class (the kernels are built for sm_100a only)";
+      tor_ctx_destroy(ctx);
+      return TOR_ERR_NO_DEVICE;
+    }
+    d.sm_count = prop.multiProcessorCount;
+    d.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    bool ok = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&d.ev0) == cudaSuccess && cudaEventCreate(&d.ev1) == cudaSuccess &&
+              cudaMalloc(&d.d_work, sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&d.d_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMemset(d.d_counters, 0, 2 * sizeof(unsigned long long)) == cudaSuccess;
+    ctx->devs.push_back(d);
+    if (!ok) {
+      g_create_err = std::string("context allocation: ") + cudaGetErrorString(cudaGetLastError());
+      tor_ctx_destroy(ctx);
+      return TOR_ERR_CUDA;
+    }
+  }
+  *out = ctx;
+  return TOR_OK;
+}
+
+void tor_ctx_destroy(tor_ctx* ctx) {
+  if (!ctx) return;
+  for (DeviceState& d : ctx->devs) {
+    cudaSetDevice(d.dev);
+    if (d.stream) cudaStreamSynchronize(d.stream);
+    if (d.d_blob) cudaFree(d.d_blob);
+    if (d.d_pixels) cudaFree(d.d_pixels);
+    if (d.d_work) cudaFree(d.d_work);
+    if (d.d_counters) cudaFree(d.d_counters);
+    if (d.ev0) cudaEventDestroy(d.ev0);
+    if (d.ev1) cudaEventDestroy(d.ev1);
+    if (d.stream) cudaStreamDestroy(d.stream);
+  }
+  delete ctx;
+}
+
+int tor_scene_upload(tor_ctx* ctx, const tor_camera* cam, const void* objects, int64_t len, int64_t stride) {
+  if (!ctx) return TOR_ERR_INVALID_ARG;
+  int rc = set_scene(ctx, cam, objects, len, stride);
+  if (rc) return rc;
+  return upload_scene_to(ctx, ctx->devs[0]);
+}
+
+int tor_render_device_async(tor_ctx* ctx, double* d_pixels, int32_t nrows, int32_t ncols, int32_t samples_per_pixel,
+                            float gamma_correction, int64_t max_depth, uint32_t flags, int32_t row_begin,
+                            int32_t row_end, int32_t row_step, void* cuda_stream) {
+  if (!ctx) return TOR_ERR_INVALID_ARG;
+  if (!ctx->have_scene) return fail(ctx, TOR_ERR_INVALID_ARG, "tor_scene_upload has not been called");
+  if (!d_pixels) return fail(ctx, TOR_ERR_INVALID_ARG, "d_pixels is NULL");
+  int rc = check_canvas_dims(ctx, nrows, ncols, samples_per_pixel, max_depth, row_begin, row_end, row_step);
+  if (rc) return rc;
+  DeviceState& d = ctx->devs[0];
+  rc = upload_scene_to(ctx, d);
+  if (rc) return rc;
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : d.stream;
+  return launch_rows(ctx, d, d_pixels, nrows, ncols, samples_per_pixel, gamma_correction, max_depth, flags, row_begin,
+                     row_end, row_step, s, /*timed=*/true);
+}
+
+int tor_sync(tor_ctx* ctx) {
+  if (!ctx) return TOR_ERR_INVALID_ARG;
+  for (DeviceState& d : ctx->devs) {
+    TOR_CUDA(ctx, cudaSetDevice(d.dev));
+    TOR_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  }
+  return TOR_OK;
+}
+
+int tor_render_rows(tor_ctx* ctx, tor_canvas* canvas, const tor_camera* cam, const void* objects, int64_t len,
+                    int64_t stride, int64_t max_depth, uint32_t flags, int32_t row_begin, int32_t row_end,
+                    int32_t row_step) {
+  if (!ctx) return TOR_ERR_INVALID_ARG;
+  if (!canvas || !canvas->pixels) return fail(ctx, TOR_ERR_INVALID_ARG, "canvas or canvas->pixels is NULL");
+  int rc = check_canvas_dims(ctx, canvas->nrows, canvas->ncols, canvas->samples_per_pixel, max_depth, row_begin,
+                             row_end, row_step);
+  if (rc) return rc;
+  rc = set_scene(ctx, cam, objects, len, stride);
+  if (rc) return rc;
+
+  const int ndev = (int)ctx->devs.size();
+  const int32_t ncols = canvas->ncols;
+  const size_t row_bytes = (size_t)ncols * 3 * sizeof(double);
+  const int32_t nsel_total = row_end > row_begin ? (row_end - row_begin + row_step - 1) / row_step : 0;
+  if (nsel_total == 0) return TOR_OK;
+
+  // selected row k (k = 0 .. nsel_total-1) goes to device k mod ndev: cheap sky rows and expensive
+  // ground rows interleave across devices.  Seeds use the absolute (row, col), so the image does not
+  // depend on ndev (render.nim:59-60).
+  for (int g = 0; g < ndev; ++g) {
+    DeviceState& d = ctx->devs[g];
+    if (g >= nsel_total) {
+      d.timed = false;
+      continue;
+    }
+    const int32_t rb = row_begin + g * row_step;
+    const int32_t rs = row_step * ndev;
+    const int32_t nsel = (row_end - rb + rs - 1) / rs;
+    rc = ensure_capacity(ctx, d, ctx->scene.blob.size(), (size_t)nsel * row_bytes);
+    if (rc) return rc;
+    rc = upload_scene_to(ctx, d);
+    if (rc) return rc;
+    rc = launch_rows(ctx, d, d.d_pixels, canvas->nrows, ncols, canvas->samples_per_pixel, canvas->gamma_correction,
+                     max_depth, flags, rb, row_end, rs, d.stream, /*timed=*/true);
+    if (rc) return rc;
+    // device rows are compact; scatter them back to their canvas rows (pitch = rs rows)
+    double* dst = canvas->pixels + (size_t)rb * ncols * 3;
+    TOR_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)rs * row_bytes, d.d_pixels, row_bytes, row_bytes, (size_t)nsel,
+                                    cudaMemcpyDeviceToHost, d.stream));
+  }
+  return tor_sync(ctx);
+}
+
+int tor_render(tor_ctx* ctx, tor_canvas* canvas, const tor_camera* cam, const void* objects, int64_t len,
+               int64_t stride, int64_t max_depth, uint32_t flags) {
+  if (!ctx) return TOR_ERR_INVALID_ARG;
+  if (!canvas) return fail(ctx, TOR_ERR_INVALID_ARG, "canvas is NULL");
+  return tor_render_rows(ctx, canvas, cam, objects, len, stride, max_depth, flags, 0, canvas->nrows, 1);
+}
+
+int tor_get_counters(tor_ctx* ctx, uint64_t out[3]) {
+  if (!ctx || !out) return TOR_ERR_INVALID_ARG;
+  uint64_t rays = 0, segs = 0;
+  for (DeviceState& d : ctx->devs) {
+    unsigned long long h[2] = {0, 0};
+    TOR_CUDA(ctx, cudaSetDevice(d.dev));
+    TOR_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    TOR_CUDA(ctx, cudaMemcpy(h, d.d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    TOR_CUDA(ctx, cudaMemset(d.d_counters, 0, sizeof(h)));
+    rays += h[0];
+    segs += h[1];
+  }
+  out[0] = rays;
+  out[1] = segs;
+  out[2] = segs * (uint64_t)(ctx->have_scene ? ctx->scene.view.n_objects : 0);
+  ctx->counters_pending = false;
+  return TOR_OK;
+}
+
+int tor_last_kernel_ms(tor_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return TOR_ERR_INVALID_ARG;
+  float mx = 0.f;
+  bool any = false;
+  for (DeviceState& d : ctx->devs) {
+    if (!d.timed) continue;
+    float t = 0.f;
+    TOR_CUDA(ctx, cudaSetDevice(d.dev));
+    TOR_CUDA(ctx, cudaEventSynchronize(d.ev1));
+    TOR_CUDA(ctx, cudaEventElapsedTime(&t, d.ev0, d.ev1));
+    if (t > mx) mx = t;
+    any = true;
+  }
+  if (!any) return fail(ctx, TOR_ERR_INVALID_ARG, "no render has been timed on this context");
+  *ms = mx;
+  return TOR_OK;
+}
+
+int64_t tor_launch_count(const tor_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+// tor_host.cc — host-side helpers of include/tor_b200.h that restate the reference's constructors and
+// output format (camera(), random_scene(), exportToPPM).  They are inputs / outputs either side of the
+// render path, not the path itself; nothing here touches the GPU.
+//
+// Built with -ffp-contract=off so the float64 results are the reference's (scalar SSE2, no FMA).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/tor_b200.h"
+
+namespace {
+
+// ---- support/rng.nim:18-74,116-143 (host copy for the scene generators) ----
+struct HostRng {
+  uint64_t s[4];
+  static uint64_t splitmix(uint64_t& st) {  // rng.nim:31-36 — first multiplier used twice (sic)
+    st += 0x9e3779b97f4a7c15ull;
+    uint64_t z = st;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0xbf58476d1ce4e5b9ull;
+    return z ^ (z >> 31);
+  }
+  explicit HostRng(uint64_t seed) {  // rng.nim:38-44
+    for (int i = 0; i < 4; ++i) s[i] = splitmix(seed);
+  }
+  uint64_t next() {  // rng.nim:58-74
+    uint64_t r = s[0] + s[3], t = s[1] << 17;
+    s[2] ^= s[0];
+    s[3] ^= s[1];
+    s[1] ^= s[2];
+    s[0] ^= s[3];
+    s[2] ^= t;
+    s[3] = (s[3] << 45) | (s[3] >> 19);
+    return r;
+  }
+  double u01() {  // rng.nim:129-133
+    uint64_t b = (next() >> 12) | 0x3ff0000000000000ull;
+    double d;
+    memcpy(&d, &b, 8);
+    return d - 1.0;
+  }
+  double umax(double mx) { return u01() * mx; }  // rng.nim:135-143
+  double urange(double lo, double hi) {          // rng.nim:116-127
+    double v = u01() * (hi - lo) + lo;
+    return v <= lo ? lo : v;
+  }
+};
+
+struct V {
+  double x, y, z;
+};
+V sub(V a, V b) { return V{a.x - b.x, a.y - b.y, a.z - b.z}; }
+V mul(V a, double s) { return V{a.x * s, a.y * s, a.z * s}; }
+V cross(V a, V b) { return V{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+double len(V a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+V unit(V a) { return mul(a, 1.0 / len(a)); }  // vec3s.nim:93-94,106-107: `/` multiplies by the reciprocal
+void put(double* d, V a) {
+  d[0] = a.x;
+  d[1] = a.y;
+  d[2] = a.z;
+}
+
+tor_hittable mk_sphere(V c, double r, uint32_t mat, V albedo, double fz) {
+  tor_hittable h;
+  memset(&h, 0, sizeof(h));
+  h.kind = TOR_SPHERE;
+  h.mat_kind = mat;
+  put(h.center0, c);
+  h.radius = r;
+  put(h.albedo, albedo);
+  h.fuzz_or_ior = fz;
+  return h;
+}
+
+int ppm_level(double c) {  // io/ppm.nim:15-16 + safe_math.nim:10-14; NaN (UB in the reference) -> 0
+  if (c != c) return 0;
+  double cl = c < 0.0 ? 0.0 : (c > 0.999 ? 0.999 : c);
+  return (int)(256 * cl);
+}
+
+}  // namespace
+
+extern "C" {
+
+// physics/cameras.nim:24-45
+void tor_camera_make(tor_camera* out, const double look_from[3], const double look_at[3], const double view_up[3],
+                     double vfov_degrees, double aspect_ratio, double aperture, double focus_distance,
+                     double shutter_open, double shutter_close) {
+  V from{look_from[0], look_from[1], look_from[2]}, at{look_at[0], look_at[1], look_at[2]};
+  V vup{view_up[0], view_up[1], view_up[2]};
+  double theta = vfov_degrees * (3.141592653589793 / 180.0);  // std/math degToRad
+  double h = tan(theta / 2.0);
+  double viewport_height = 2.0 * h;
+  double viewport_width = aspect_ratio * viewport_height;
+  V w = unit(sub(from, at));
+  V u = unit(cross(vup, w));
+  V v = cross(w, u);
+  V horizontal = mul(u, focus_distance * viewport_width);
+  V vertical = mul(v, focus_distance * viewport_height);
+  V llc = sub(sub(sub(from, mul(horizontal, 1.0 / 2)), mul(vertical, 1.0 / 2)), mul(w, focus_distance));
+  put(out->origin, from);
+  put(out->lower_left_corner, llc);
+  put(out->horizontal, horizontal);
+  put(out->vertical, vertical);
+  put(out->u, u);
+  put(out->v, v);
+  put(out->w, w);
+  out->lens_radius = aperture / 2;
+  out->shutter_open = shutter_open;
+  out->shutter_close = shutter_close;
+}
+
+// scenes.nim:13-50 (draw order: SURVEY.md appendix B)
+int64_t tor_random_scene(uint64_t seed, int32_t half, tor_hittable* out, int64_t cap) {
+  HostRng rng(seed);
+  std::vector<tor_hittable> w;
+  w.push_back(mk_sphere(V{0, -1000, 0}, 1000, TOR_LAMBERTIAN, V{0.5, 0.5, 0.5}, 0));
+  for (int a = -half; a < half; ++a)
+    for (int b = -half; b < half; ++b) {
+      double cx = (double)a + 0.9 * rng.u01();
+      double cz = (double)b + 0.9 * rng.u01();
+      V center{cx, 0.2, cz};
+      if (len(sub(center, V{4, 0.2, 0})) > 0.9) {
+        double choose = rng.u01();
+        if (choose < 0.8) {  // diffuse: a *moving* sphere at this commit (scenes.nim:32-36)
+          V a1{0, 0, 0}, a2{0, 0, 0};
+          a1.x = rng.u01(); a1.y = rng.u01(); a1.z = rng.u01();
+          a2.x = rng.u01(); a2.y = rng.u01(); a2.z = rng.u01();
+          tor_hittable h = mk_sphere(center, 0.2, TOR_LAMBERTIAN, V{a1.x * a2.x, a1.y * a2.y, a1.z * a2.z}, 0);
+          h.kind = TOR_MOVING_SPHERE;
+          put(h.center1, V{center.x + 0, center.y + rng.umax(0.5), center.z + 0});
+          h.time0 = 0.0;
+          h.time1 = 1.0;
+          w.push_back(h);
+        } else if (choose < 0.95) {
+          V albedo{0, 0, 0};
+          albedo.x = rng.urange(0.5, 1); albedo.y = rng.urange(0.5, 1); albedo.z = rng.urange(0.5, 1);
+          double fuzz = rng.umax(0.5);
+          w.push_back(mk_sphere(center, 0.2, TOR_METAL, albedo, fuzz <= 1.0 ? fuzz : 1.0));  // materials.nim:35-37
+        } else {
+          w.push_back(mk_sphere(center, 0.2, TOR_DIELECTRIC, V{0, 0, 0}, 1.5));
+        }
+      }
+    }
+  w.push_back(mk_sphere(V{0, 1, 0}, 1.0, TOR_DIELECTRIC, V{0, 0, 0}, 1.5));
+  w.push_back(mk_sphere(V{-4, 1, 0}, 1.0, TOR_LAMBERTIAN, V{0.4, 0.2, 0.1}, 0));
+  w.push_back(mk_sphere(V{4, 1, 0}, 1.0, TOR_METAL, V{0.7, 0.6, 0.5}, 0.0));
+  int64_t n = (int64_t)w.size();
+  if (out)
+    for (int64_t i = 0; i < n && i < cap; ++i) out[i] = w[(size_t)i];
+  return n;
+}
+
+// io/ppm.nim:14-27
+int tor_quantise_rgb8(const tor_canvas* canvas, uint8_t* out) {
+  if (!canvas || !canvas->pixels || !out) return TOR_ERR_INVALID_ARG;
+  int64_t k = 0;
+  for (int32_t i = canvas->nrows - 1; i >= 0; --i)
+    for (int32_t j = 0; j < canvas->ncols; ++j) {
+      const double* p = canvas->pixels + 3 * ((int64_t)i * canvas->ncols + j);
+      out[k++] = (uint8_t)ppm_level(p[0]);
+      out[k++] = (uint8_t)ppm_level(p[1]);
+      out[k++] = (uint8_t)ppm_level(p[2]);
+    }
+  return TOR_OK;
+}
+
+int tor_export_ppm(const tor_canvas* canvas, const char* path) {
+  if (!canvas || !canvas->pixels || !path) return TOR_ERR_INVALID_ARG;
+  FILE* f = fopen(path, "wb");
+  if (!f) return TOR_ERR_INVALID_ARG;
+  fprintf(f, "P3\n%d %d\n255\n", canvas->ncols, canvas->nrows);
+  std::string line;
+  for (int32_t i = canvas->nrows - 1; i >= 0; --i) {
+    line.clear();
+    for (int32_t j = 0; j < canvas->ncols; ++j) {
+      const double* p = canvas->pixels + 3 * ((int64_t)i * canvas->ncols + j);
+      char buf[48];
+      int n = snprintf(buf, sizeof(buf), "%d %d %d\n", ppm_level(p[0]), ppm_level(p[1]), ppm_level(p[2]));
+      line.append(buf, (size_t)n);
+    }
+    fwrite(line.data(), 1, line.size(), f);
+  }
+  fclose(f);
+  return TOR_OK;
+}
+
+}  // extern "C"
