@@ -42,7 +42,7 @@ TOR_FLAG_COUNT_SEGMENTS = 0x100
 EXPORTED_SYMBOLS = [
     "tor_abi_version", "tor_ctx_create", "tor_ctx_destroy", "tor_last_error", "tor_render", "tor_render_rows",
     "tor_scene_upload", "tor_render_device_async", "tor_sync", "tor_get_counters", "tor_last_kernel_ms",
-    "tor_launch_count", "tor_camera_make", "tor_random_scene", "tor_export_ppm", "tor_quantise_rgb8",
+    "tor_launch_count", "tor_measure_fp64_peak", "tor_camera_make", "tor_random_scene", "tor_export_ppm", "tor_quantise_rgb8",
 ]
 
 
@@ -98,6 +98,7 @@ def load_library():
     L.tor_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.tor_launch_count.argtypes = [vp]
     L.tor_launch_count.restype = C.c_int64
+    L.tor_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.tor_camera_make.argtypes = [C.POINTER(_CCamera)] + [C.POINTER(C.c_double)] * 3 + [C.c_double] * 6
     L.tor_camera_make.restype = None
     L.tor_random_scene.argtypes = [C.c_uint64, C.c_int32, vp, C.c_int64]
@@ -304,7 +305,12 @@ class Context:
         self._check(self.L.tor_scene_upload(self.h, C.byref(cam.c), objs.ctypes.data, len(objs), objs.dtype.itemsize))
 
     def render_device_async(self, d_pixels_ptr, nrows, ncols, spp, gamma, max_depth, flags=0, rows=None, stream=None):
+        """stream: a cudaStream_t handle as int (e.g. torch.cuda.current_stream().cuda_stream) or None for the
+        context's own stream.  Handle 0 is CUDA's legacy default stream and is passed as cudaStreamLegacy (0x1),
+        because the C ABI reserves NULL for "the context's stream"."""
         rb, re, rs = rows if rows is not None else (0, nrows, 1)
+        if stream is not None and int(stream) == 0:
+            stream = 1  # cudaStreamLegacy
         self._check(self.L.tor_render_device_async(self.h, d_pixels_ptr, nrows, ncols, spp, float(np.float32(gamma)),
                                                    max_depth, flags, rb, re, rs, stream))
 
@@ -320,6 +326,12 @@ class Context:
         ms = C.c_float()
         self._check(self.L.tor_last_kernel_ms(self.h, C.byref(ms)))
         return float(ms.value)
+
+    def measure_fp64_peak(self):
+        """Sustained FP64 FMA instructions per second per GPU (lane-level), from a register-only DFMA loop."""
+        v = C.c_double()
+        self._check(self.L.tor_measure_fp64_peak(self.h, C.byref(v)))
+        return float(v.value)
 
     def launch_count(self):
         return int(self.L.tor_launch_count(self.h))

@@ -393,4 +393,33 @@ int tor_last_kernel_ms(tor_ctx* ctx, float* ms) {
 
 int64_t tor_launch_count(const tor_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int tor_measure_fp64_peak(tor_ctx* ctx, double* dfma_per_second) {
+  if (!ctx || !dfma_per_second) return TOR_ERR_INVALID_ARG;
+  DeviceState& d = ctx->devs[0];
+  TOR_CUDA(ctx, cudaSetDevice(d.dev));
+  double* sink = nullptr;
+  TOR_CUDA(ctx, cudaMalloc(&sink, sizeof(double)));
+  const int iters = 4096, grid = d.sm_count * 8, block = 256;
+  cudaEvent_t e0, e1;
+  TOR_CUDA(ctx, cudaEventCreate(&e0));
+  TOR_CUDA(ctx, cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+    TOR_CUDA(ctx, cudaEventRecord(e0, d.stream));
+    tor::fp64_peak_kernel<<<grid, block, 0, d.stream>>>(sink, iters, 1.0000001, 1e-9);
+    TOR_CUDA(ctx, cudaEventRecord(e1, d.stream));
+    TOR_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    TOR_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    double rate = (double)grid * block * (double)iters * tor::kPeakChains / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+    ctx->launches += 1;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *dfma_per_second = best;
+  return TOR_OK;
+}
+
 }  // extern "C"

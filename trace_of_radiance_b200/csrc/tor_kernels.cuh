@@ -482,4 +482,21 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_exact_kernel(const 
   }
 }
 
+// ------------------------------------------------------------------- FP64 peak microbenchmark
+// Register-only DFMA chains: the denominator of the ALU roofline (MEASURED_PEAKS.json has no FP64 entry).
+static constexpr int kPeakChains = 16;
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters, double m, double c) {
+  double acc[kPeakChains];
+#pragma unroll
+  for (int k = 0; k < kPeakChains; ++k) acc[k] = (double)(threadIdx.x + k);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < kPeakChains; ++k) acc[k] = fma(acc[k], m, c);
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < kPeakChains; ++k) s += acc[k];
+  if (s == 12345.678) *sink = s;  // never true; keeps the chains alive
+}
+
 }  // namespace tor
