@@ -1,0 +1,417 @@
+// tor_bvh.hpp — host-side build of the bounding-volume hierarchy the render kernel traverses.
+//
+// The reference scans every object for every bounce segment (physics/hittables/hittables_lists.nim:48-55;
+// README.md:36-37 notes the missing acceleration structure).  The closest hit of that scan is
+//     argmin over objects of (t_i, i)   with t_i = the object's first root in (t_min, +inf)
+// (see tor_kernels.cuh), so ANY superset of the objects that can have a root may be tested, in any order,
+// and the result is bit-identical.  The hierarchy only has to be conservative:
+//
+//   * every object's box covers the sphere at every time a ray can carry (camera shutter interval and
+//     the 0.0 that Metal / Dielectric scattering resets to, rays.nim:19), and is padded by 2^-19 of the
+//     scene's largest coordinate — this absorbs (a) the float32 rounding of the slab test
+//     (<= 2^-20.4 * S in position, derivation in DESIGN.md §bvh) and (b) the reference's own float64
+//     rounding (~2^-45 * S);
+//   * boxes are stored in float32 rounded OUTWARD;
+//   * objects whose box is not finite (NaN / inf centres, zero-length time interval) are not put in the
+//     tree at all: they sit in an "always" list that every segment tests exactly.
+//
+// Blob layout:  [BvhNode x n_nodes][ObjRec x n_objects (tree leaves first, then the "always" list)]
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/tor_b200.h"
+#include "tor_scene_pack.hpp"
+
+namespace tor {
+
+// Two children per node, each with its own box.  child >= 0: inner node index; child < 0: leaf,
+// v = ~child, first record = v >> 4, count = v & 15 (0 = empty child).
+struct alignas(16) BvhNode {  // 64 bytes
+  float lo0[3], hi0[3];
+  float lo1[3], hi1[3];
+  int32_t child0, child1;
+  int32_t pad[2];
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode layout");
+
+// Everything the kernel needs about one object, in leaf order.  Derived fields are the SAME IEEE operations
+// the reference performs on the same inputs (so precomputing them changes no bit):
+//   dc = center1 - center0 (moving_spheres.nim:43), r2 = radius*radius (spheres.nim:32),
+//   inv_r = 1.0/radius (spheres.nim:43 through vec3s.nim:93-94).
+struct alignas(16) ObjRec {  // 128 bytes
+  double c0[3];
+  double r2m;  // filter: r^2 inflated by the conservative slack (tor_scene_pack.hpp)
+  double dc[3];
+  double r2;
+  double t0, t1;  // time0, time1 (static spheres: 0, 1 and dc = 0)
+  double albedo[3];
+  double fuzz_or_ior;
+  double inv_r;
+  uint32_t kind_mat;  // kind | mat_kind << 8
+  uint32_t orig;      // index in the caller's HittableList (ties go to the lowest, hittables_lists.nim:48-55)
+};
+static_assert(sizeof(ObjRec) == 128, "ObjRec layout");
+
+struct BvhView {  // kernel parameter
+  int32_t n_nodes;
+  int32_t n_tree_objs;    // records [0, n_tree_objs) are reachable through the tree
+  int32_t n_objects;      // records [n_tree_objs, n_objects) are the "always" list
+  int32_t has_movers;
+  uint32_t off_nodes, off_objs;
+  uint32_t nodes_bytes;   // blob prefix holding the nodes
+  uint32_t total_bytes;
+};
+
+struct PackedBvh {
+  BvhView view;
+  std::vector<uint8_t> blob;
+  int max_depth = 0;
+  int n_leaves = 0;
+};
+
+static constexpr int kBvhMaxLeaf = 4;
+static constexpr int kBvhStackDepth = 40;  // >= max tree depth (forced median splits below bound it)
+
+namespace bvh_detail {
+
+struct Box {
+  double lo[3], hi[3];
+};
+struct Prim {
+  Box b;
+  double c[3];
+  int obj;
+};
+
+inline void box_reset(Box& b) {
+  for (int k = 0; k < 3; ++k) {
+    b.lo[k] = INFINITY;
+    b.hi[k] = -INFINITY;
+  }
+}
+inline void box_grow(Box& b, const Box& o) {
+  for (int k = 0; k < 3; ++k) {
+    if (o.lo[k] < b.lo[k]) b.lo[k] = o.lo[k];
+    if (o.hi[k] > b.hi[k]) b.hi[k] = o.hi[k];
+  }
+}
+inline double box_area(const Box& b) {
+  double dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+  if (!(dx >= 0 && dy >= 0 && dz >= 0)) return 0.0;
+  return 2.0 * (dx * dy + dy * dz + dz * dx);
+}
+inline float f32_down(double v) {
+  float f = (float)v;
+  if ((double)f > v) f = nextafterf(f, -INFINITY);
+  return nextafterf(f, -INFINITY);
+}
+inline float f32_up(double v) {
+  float f = (float)v;
+  if ((double)f < v) f = nextafterf(f, INFINITY);
+  return nextafterf(f, INFINITY);
+}
+
+struct Builder {
+  std::vector<Prim>& prims;
+  std::vector<BvhNode>& nodes;
+  std::vector<int>& order;  // object indices in leaf order
+  double pad;
+  int max_depth = 0;
+  int n_leaves = 0;
+
+  void store_box(float* lo, float* hi, const Box& b) {
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = f32_down(b.lo[k] - pad);
+      hi[k] = f32_up(b.hi[k] + pad);
+    }
+  }
+  static void store_empty(float* lo, float* hi) {
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = 3.0e38f;
+      hi[k] = -3.0e38f;
+    }
+  }
+  int32_t make_leaf(int begin, int end) {
+    int first = (int)order.size();
+    // ascending original index inside a leaf (not required for correctness; keeps runs deterministic)
+    std::sort(prims.begin() + begin, prims.begin() + end, [](const Prim& a, const Prim& b) { return a.obj < b.obj; });
+    for (int i = begin; i < end; ++i) order.push_back(prims[(size_t)i].obj);
+    ++n_leaves;
+    return ~(int32_t)((first << 4) | (end - begin));
+  }
+
+  // Chooses a split of prims[begin, end) (count > 1); returns mid, or -1 to make a leaf.
+  int split(int begin, int end, int depth) {
+    const int n = end - begin;
+    Box cb;
+    box_reset(cb);
+    Box all;
+    box_reset(all);
+    for (int i = begin; i < end; ++i) {
+      const Prim& p = prims[(size_t)i];
+      for (int k = 0; k < 3; ++k) {
+        if (p.c[k] < cb.lo[k]) cb.lo[k] = p.c[k];
+        if (p.c[k] > cb.hi[k]) cb.hi[k] = p.c[k];
+      }
+      box_grow(all, p.b);
+    }
+    int axis = 0;
+    double ext = cb.hi[0] - cb.lo[0];
+    for (int k = 1; k < 3; ++k)
+      if (cb.hi[k] - cb.lo[k] > ext) {
+        ext = cb.hi[k] - cb.lo[k];
+        axis = k;
+      }
+    auto median = [&](int ax) {
+      int mid = begin + n / 2;
+      std::nth_element(prims.begin() + begin, prims.begin() + mid, prims.begin() + end,
+                       [ax](const Prim& a, const Prim& b) { return a.c[ax] < b.c[ax] || (a.c[ax] == b.c[ax] && a.obj < b.obj); });
+      return mid;
+    };
+    if (!(ext > 0.0)) return n <= kBvhMaxLeaf ? -1 : median(axis);  // coincident centroids
+    if (depth >= 16) return n <= kBvhMaxLeaf ? -1 : median(axis);   // bounds the depth: <= 16 + log2(65536/leaf)
+
+    // binned surface-area heuristic on every axis
+    constexpr int kBins = 16;
+    const double c_trav = 1.0, c_isect = 0.7;
+    double best_cost = INFINITY;
+    int best_axis = -1, best_bin = -1;
+    for (int ax = 0; ax < 3; ++ax) {
+      double e = cb.hi[ax] - cb.lo[ax];
+      if (!(e > 0.0)) continue;
+      Box bb[kBins];
+      int cnt[kBins];
+      for (int b = 0; b < kBins; ++b) {
+        box_reset(bb[b]);
+        cnt[b] = 0;
+      }
+      const double scale = kBins / e;
+      for (int i = begin; i < end; ++i) {
+        const Prim& p = prims[(size_t)i];
+        int b = (int)((p.c[ax] - cb.lo[ax]) * scale);
+        if (b < 0) b = 0;
+        if (b >= kBins) b = kBins - 1;
+        box_grow(bb[b], p.b);
+        ++cnt[b];
+      }
+      double right_area[kBins];
+      int right_cnt[kBins];
+      Box acc;
+      box_reset(acc);
+      int c = 0;
+      for (int b = kBins - 1; b > 0; --b) {
+        box_grow(acc, bb[b]);
+        c += cnt[b];
+        right_area[b] = box_area(acc);
+        right_cnt[b] = c;
+      }
+      box_reset(acc);
+      c = 0;
+      for (int b = 0; b < kBins - 1; ++b) {
+        box_grow(acc, bb[b]);
+        c += cnt[b];
+        if (c == 0 || right_cnt[b + 1] == 0) continue;
+        double cost = box_area(acc) * c + right_area[b + 1] * right_cnt[b + 1];
+        if (cost < best_cost) {
+          best_cost = cost;
+          best_axis = ax;
+          best_bin = b;
+        }
+      }
+    }
+    const double parent_area = box_area(all);
+    if (best_axis < 0) return n <= kBvhMaxLeaf ? -1 : median(axis);
+    if (n <= kBvhMaxLeaf && parent_area > 0.0) {
+      double split_cost = c_trav + c_isect * best_cost / parent_area;
+      if (split_cost >= c_isect * n) return -1;
+    }
+    const double lo = cb.lo[best_axis], scale = kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+    const int ax = best_axis, bin = best_bin;
+    auto it = std::partition(prims.begin() + begin, prims.begin() + end, [=](const Prim& p) {
+      int b = (int)((p.c[ax] - lo) * scale);
+      if (b < 0) b = 0;
+      if (b >= kBins) b = kBins - 1;
+      return b <= bin;
+    });
+    int mid = (int)(it - prims.begin());
+    if (mid == begin || mid == end) return median(axis);
+    return mid;
+  }
+
+  // Builds the subtree over prims[begin, end) and returns its child reference + its box.
+  int32_t build(int begin, int end, int depth, Box* out_box) {
+    box_reset(*out_box);
+    for (int i = begin; i < end; ++i) box_grow(*out_box, prims[(size_t)i].b);
+    if (depth > max_depth) max_depth = depth;
+    const int n = end - begin;
+    int mid = n == 1 ? -1 : split(begin, end, depth);
+    if (mid < 0) return make_leaf(begin, end);
+    int me = (int)nodes.size();
+    nodes.emplace_back();
+    Box b0, b1;
+    int32_t c0 = build(begin, mid, depth + 1, &b0);
+    int32_t c1 = build(mid, end, depth + 1, &b1);
+    BvhNode& nd = nodes[(size_t)me];
+    memset(&nd, 0, sizeof(nd));
+    store_box(nd.lo0, nd.hi0, b0);
+    store_box(nd.lo1, nd.hi1, b1);
+    nd.child0 = c0;
+    nd.child1 = c1;
+    return me;
+  }
+};
+
+}  // namespace bvh_detail
+
+// objects: decoded flat records.  shutter_*: the camera's interval.  Returns false with *err set on bad input.
+static inline bool pack_bvh(const std::vector<tor_hittable>& objs, const tor_camera& cam, PackedBvh* out,
+                            std::string* err) {
+  using namespace bvh_detail;
+  const int n = (int)objs.size();
+  if (n <= 0 || n > 65535) {
+    *err = "object count must be in 1..65535";
+    return false;
+  }
+  double time_lo = 0.0, time_hi = 0.0;  // rays.nim:19 — scattered Metal / Dielectric rays carry time 0.0
+  for (double t : {cam.shutter_open, cam.shutter_close}) {
+    if (t < time_lo) time_lo = t;
+    if (t > time_hi) time_hi = t;
+  }
+  const bool time_ok = isfinite(cam.shutter_open) && isfinite(cam.shutter_close);
+
+  std::vector<Prim> prims;
+  std::vector<int> always;
+  double S = 0.0;  // largest |coordinate| of any box or of the camera (ray origins live on the objects or the lens)
+  for (int k = 0; k < 3; ++k) {
+    double lens = fabs(cam.lens_radius) * (fabs(cam.u[k]) + fabs(cam.v[k]));
+    double v = fabs(cam.origin[k]) + lens;
+    if (isfinite(v) && v > S) S = v;
+  }
+  bool has_movers = false;
+  for (int i = 0; i < n; ++i) {
+    const tor_hittable& h = objs[(size_t)i];
+    Prim p;
+    p.obj = i;
+    box_reset(p.b);
+    const double r = fabs(h.radius);
+    auto grow_at = [&](double q) {
+      for (int k = 0; k < 3; ++k) {
+        double c = h.kind == TOR_MOVING_SPHERE ? h.center0[k] + q * (h.center1[k] - h.center0[k]) : h.center0[k];
+        // 1e-9 relative head-room: the reference rounds c0 + q*dc (and q itself) in float64
+        double e = r + 1e-9 * (fabs(c) + r);
+        if (!(c - e >= p.b.lo[k])) p.b.lo[k] = c - e;  // written so that NaN poisons the box
+        if (!(c + e <= p.b.hi[k])) p.b.hi[k] = c + e;
+      }
+    };
+    if (h.kind == TOR_MOVING_SPHERE) {
+      has_movers = true;
+      double q0 = (time_lo - h.time0) / (h.time1 - h.time0);
+      double q1 = (time_hi - h.time0) / (h.time1 - h.time0);
+      grow_at(q0);
+      grow_at(q1);
+      if (!time_ok) p.b.lo[0] = NAN;
+    } else {
+      grow_at(0.0);
+    }
+    bool finite = true;
+    for (int k = 0; k < 3; ++k) {
+      finite = finite && isfinite(p.b.lo[k]) && isfinite(p.b.hi[k]) && p.b.lo[k] <= p.b.hi[k];
+      finite = finite && fabs(p.b.lo[k]) < 1e30 && fabs(p.b.hi[k]) < 1e30;  // stays far from float32 overflow
+    }
+    if (!finite) {
+      always.push_back(i);
+      continue;
+    }
+    for (int k = 0; k < 3; ++k) {
+      p.c[k] = 0.5 * (p.b.lo[k] + p.b.hi[k]);
+      S = std::max(S, std::max(fabs(p.b.lo[k]), fabs(p.b.hi[k])));
+    }
+    prims.push_back(p);
+  }
+
+  std::vector<BvhNode> nodes;
+  std::vector<int> order;
+  Builder B{prims, nodes, order, /*pad=*/ldexp(S, -19)};
+  if (prims.empty()) {
+    BvhNode nd;
+    memset(&nd, 0, sizeof(nd));
+    Builder::store_empty(nd.lo0, nd.hi0);
+    Builder::store_empty(nd.lo1, nd.hi1);
+    nd.child0 = ~0;
+    nd.child1 = ~0;
+    nodes.push_back(nd);
+  } else {
+    Box rb;
+    int32_t root = B.build(0, (int)prims.size(), 0, &rb);
+    if (root < 0) {  // everything fits one leaf: wrap it in a root node
+      BvhNode nd;
+      memset(&nd, 0, sizeof(nd));
+      B.store_box(nd.lo0, nd.hi0, rb);
+      Builder::store_empty(nd.lo1, nd.hi1);
+      nd.child0 = root;
+      nd.child1 = ~0;
+      nodes.push_back(nd);
+    }
+  }
+  if (B.max_depth + 1 > kBvhStackDepth) {
+    *err = "internal: BVH deeper than the traversal stack";
+    return false;
+  }
+  const int n_tree = (int)order.size();
+  for (int i : always) order.push_back(i);
+
+  // time range for the filter slack (same bound as the brute-force filter, tor_scene_pack.hpp)
+  const double K = kFilterSlack;
+  std::vector<ObjRec> recs((size_t)n);
+  for (int j = 0; j < n; ++j) {
+    const tor_hittable& h = objs[(size_t)order[(size_t)j]];
+    ObjRec& r = recs[(size_t)j];
+    memset(&r, 0, sizeof(r));
+    const bool mover = h.kind == TOR_MOVING_SPHERE;
+    for (int k = 0; k < 3; ++k) {
+      r.c0[k] = h.center0[k];
+      r.dc[k] = mover ? h.center1[k] - h.center0[k] : 0.0;  // moving_spheres.nim:43
+      r.albedo[k] = h.albedo[k];
+    }
+    r.r2 = h.radius * h.radius;  // spheres.nim:32
+    r.inv_r = 1.0 / h.radius;    // vec3s.nim:93-94
+    r.t0 = mover ? h.time0 : 0.0;
+    r.t1 = mover ? h.time1 : 1.0;
+    r.fuzz_or_ior = h.fuzz_or_ior;
+    r.kind_mat = h.kind | (h.mat_kind << 8);
+    r.orig = (uint32_t)order[(size_t)j];
+    double ccmax;
+    if (mover) {
+      ccmax = mover_cc_bound(h, time_lo, time_hi);
+    } else {
+      ccmax = h.center0[0] * h.center0[0] + h.center0[1] * h.center0[1] + h.center0[2] * h.center0[2];
+    }
+    double r2m = r.r2 + K * (ccmax + r.r2);
+    if (!(r2m < INFINITY)) r2m = INFINITY;  // NaN / inf: the filter always passes, the exact test decides
+    r.r2m = r2m;
+  }
+
+  BvhView& v = out->view;
+  v.n_nodes = (int32_t)nodes.size();
+  v.n_tree_objs = n_tree;
+  v.n_objects = n;
+  v.has_movers = has_movers ? 1 : 0;
+  v.off_nodes = 0;
+  v.nodes_bytes = (uint32_t)(nodes.size() * sizeof(BvhNode));
+  v.off_objs = v.nodes_bytes;
+  v.total_bytes = v.off_objs + (uint32_t)(recs.size() * sizeof(ObjRec));
+  out->blob.assign(v.total_bytes, 0);
+  memcpy(out->blob.data() + v.off_nodes, nodes.data(), v.nodes_bytes);
+  memcpy(out->blob.data() + v.off_objs, recs.data(), recs.size() * sizeof(ObjRec));
+  out->max_depth = B.max_depth;
+  out->n_leaves = B.n_leaves;
+  return true;
+}
+
+}  // namespace tor

@@ -162,6 +162,135 @@ __device__ __forceinline__ double exact_first_root(const tor_hittable* __restric
   return t;
 }
 
+
+// ------------------------------------------------------------------ per-lane path state + helpers
+// Shared by the brute-force kernel below and the BVH kernel (tor_kernels_bvh.cuh): ONE restatement of
+// render.nim:62-67 (sample start), cameras.nim:47-57 and materials.nim:24-86 on the device.
+struct Lane {
+  Rng rng;
+  V3 pix, att, o, d;
+  double time;
+  int32_t row, col, sample, depth;
+};
+
+// render.nim:64-66 + cameras.nim:47-57: jitter, lens sample, shutter time -> primary ray
+__device__ __forceinline__ void start_sample(Lane& L, const tor_camera& cam, int32_t nrows, int32_t ncols) {
+  double u = ((double)L.col + rng_u01(L.rng)) / (double)(ncols - 1);
+  double v = ((double)L.row + rng_u01(L.rng)) / (double)(nrows - 1);
+  double rx, ry;
+  for (;;) {  // sampling.nim:64-68
+    rx = rng_urange(L.rng, -1.0, 1.0);
+    ry = rng_urange(L.rng, -1.0, 1.0);
+    if (rx * rx + ry * ry + 0.0 * 0.0 < 1) break;
+  }
+  double rdx = rx * cam.lens_radius, rdy = ry * cam.lens_radius;  // Vec3 * scalar
+  V3 cu = v3(cam.u[0], cam.u[1], cam.u[2]), cv = v3(cam.v[0], cam.v[1], cam.v[2]);
+  V3 offset = cu * rdx + cv * rdy;
+  V3 org = v3(cam.origin[0], cam.origin[1], cam.origin[2]);
+  V3 llc = v3(cam.lower_left_corner[0], cam.lower_left_corner[1], cam.lower_left_corner[2]);
+  V3 hor = v3(cam.horizontal[0], cam.horizontal[1], cam.horizontal[2]);
+  V3 ver = v3(cam.vertical[0], cam.vertical[1], cam.vertical[2]);
+  L.o = org + offset;
+  L.d = (((llc + u * hor) + v * ver) - org) - offset;
+  L.time = rng_urange(L.rng, cam.shutter_open, cam.shutter_close);
+  L.att = v3(1, 1, 1);
+  L.depth = 0;
+}
+
+// The surface the closest hit landed on, as the materials need it.
+struct Surface {
+  V3 center;  // at the ray's time (moving_spheres.nim:61 recomputes it on the accepted root)
+  double inv_r;
+  V3 albedo;
+  double fuzz_or_ior;
+  uint32_t mat_kind;
+};
+
+// Record fill (spheres.nim:41-46, core.nim:47-49) + scatter (materials.nim:24-86) + render.nim:35-38.
+// Returns true when the sample ends here (absorbed, or depth exhausted -> black).
+__device__ __forceinline__ bool shade_hit(Lane& L, double best_t, const Surface& S, int32_t max_depth) {
+  const V3 o = L.o, d = L.d;
+  V3 p = o + best_t * d;
+  V3 outward = (p - S.center) * S.inv_r;
+  bool front_face = dot(d, outward) < 0;  // core.nim:47-49
+  V3 n = front_face ? outward : -outward;
+  bool scattered = true;
+  V3 nd;
+  double ntime = 0.0;  // rays.nim:19 default time (Metal / Dielectric)
+  V3 matt = v3(1, 1, 1);
+  if (S.mat_kind == TOR_LAMBERTIAN) {  // materials.nim:24-30 + sampling.nim:51-55
+    double ang = rng_umax(L.rng, 6.283185307179586);
+    double z = rng_urange(L.rng, -1.0, 1.0);
+    double r = sqrt(1.0 - z * z);
+    double sn, cs;
+    detmath::sincos(ang, &sn, &cs);
+    nd = n + v3(r * cs, r * sn, z);
+    ntime = L.time;
+    matt = S.albedo;
+  } else if (S.mat_kind == TOR_METAL) {  // materials.nim:39-47
+    V3 refl = reflect(unit_vector(d), n);
+    V3 s;
+    for (;;) {  // sampling.nim:45-49
+      s.x = rng_urange(L.rng, -1, 1);
+      s.y = rng_urange(L.rng, -1, 1);
+      s.z = rng_urange(L.rng, -1, 1);
+      if (len2(s) < 1.0) break;
+    }
+    nd = refl + S.fuzz_or_ior * s;
+    scattered = dot(nd, n) > 0;
+    matt = S.albedo;
+  } else {  // materials.nim:62-86
+    double ior = S.fuzz_or_ior;
+    double eta = front_face ? 1.0 / ior : ior;
+    V3 ud = unit_vector(d);
+    double dt = dot(-ud, n);
+    double cos_theta = (dt <= 1.0) ? dt : 1.0;
+    double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
+    bool do_reflect = eta * sin_theta > 1.0;
+    if (!do_reflect) {
+      double r0 = (1 - eta) / (1 + eta);  // schlick, materials.nim:55-60
+      r0 *= r0;
+      double reflect_prob = r0 + (1 - r0) * detmath::pow(1 - cos_theta, 5.0);
+      do_reflect = rng_u01(L.rng) < reflect_prob;
+    }
+    if (do_reflect) {
+      nd = reflect(ud, n);
+    } else {  // rays.nim:30-37
+      double ct = dot(-ud, n);
+      V3 r_par = eta * (ud + ct * n);
+      V3 r_perp = (-sqrt(1.0 - len2(r_par))) * n;
+      nd = r_par + r_perp;
+    }
+  }
+  if (!scattered) return true;  // render.nim:38 -> black
+  L.att.x *= matt.x;            // render.nim:35-37
+  L.att.y *= matt.y;
+  L.att.z *= matt.z;
+  L.o = p;
+  L.d = nd;
+  L.time = ntime;
+  ++L.depth;
+  return L.depth >= max_depth;  // render.nim:47 -> black
+}
+
+// render.nim:40-45 — the ray left the scene: sky colour times the attenuation so far
+__device__ __forceinline__ V3 shade_miss(const Lane& L) {
+  V3 ud = unit_vector(L.d);
+  double t = 0.5 * ud.y + 1.0;
+  V3 color = v3((1.0 - t) + t * 0.5, (1.0 - t) + t * 0.7, (1.0 - t) + t);
+  color.x *= L.att.x;
+  color.y *= L.att.y;
+  color.z *= L.att.z;
+  return color;
+}
+
+// canvas.nim:47-54 `draw`
+__device__ __forceinline__ void draw_pixel(double* out, V3 pix, double inv_spp, double inv_gamma) {
+  out[0] = detmath::pow(inv_spp * pix.x, inv_gamma);
+  out[1] = detmath::pow(inv_spp * pix.y, inv_gamma);
+  out[2] = detmath::pow(inv_spp * pix.z, inv_gamma);
+}
+
 // ------------------------------------------------------------------------------ the kernel
 // STAGE: 2 = whole blob staged in shared memory; 1 = filter records only; 0 = nothing (scene too large)
 template <int BLOCK, int STAGE>
@@ -209,14 +338,14 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_exact_kernel(const 
   const unsigned long long total_px = (unsigned long long)P.nsel_rows * (unsigned long long)P.ncols;
 
   // ---- per-lane persistent state
-  Rng rng;
-  V3 pix = v3(0, 0, 0);
-  V3 att = v3(1, 1, 1);
-  V3 o = v3(0, 0, 0), d = v3(0, 0, 1);
-  double time = 0.0;
+  Lane L;
+  L.pix = v3(0, 0, 0);
+  L.att = v3(1, 1, 1);
+  L.o = v3(0, 0, 0);
+  L.d = v3(0, 0, 1);
+  L.time = 0.0;
+  L.row = L.col = L.sample = L.depth = 0;
   unsigned long long px = 0;  // index into the selected-pixel queue
-  int32_t row = 0, col = 0;
-  int32_t sample = 0, depth = 0;
   bool active = false;
   bool need_pixel = true;
   bool need_sample = false;
@@ -232,11 +361,11 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_exact_kernel(const 
         if (px >= total_px) break;
         if (P.spp > 0) {
           int32_t ri = (int32_t)(px / (unsigned long long)P.ncols);
-          col = (int32_t)(px - (unsigned long long)ri * (unsigned long long)P.ncols);
-          row = P.row_begin + ri * P.row_step;
-          rng_seed_pixel(rng, row, col);  // render.nim:59-60
-          pix = v3(0, 0, 0);
-          sample = 0;
+          L.col = (int32_t)(px - (unsigned long long)ri * (unsigned long long)P.ncols);
+          L.row = P.row_begin + ri * P.row_step;
+          rng_seed_pixel(L.rng, L.row, L.col);  // render.nim:59-60
+          L.pix = v3(0, 0, 0);
+          L.sample = 0;
           active = true;
           need_sample = true;
           break;
@@ -249,31 +378,12 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_exact_kernel(const 
     if (!__any_sync(0xffffffffu, active)) break;
 
     if (active && need_sample) {
-      // render.nim:64-66 + cameras.nim:47-57
-      double u = ((double)col + rng_u01(rng)) / (double)(P.ncols - 1);
-      double v = ((double)row + rng_u01(rng)) / (double)(P.nrows - 1);
-      double rx, ry;
-      for (;;) {  // sampling.nim:64-68
-        rx = rng_urange(rng, -1.0, 1.0);
-        ry = rng_urange(rng, -1.0, 1.0);
-        if (rx * rx + ry * ry + 0.0 * 0.0 < 1) break;
-      }
-      const tor_camera& cam = P.cam;
-      double rdx = rx * cam.lens_radius, rdy = ry * cam.lens_radius;  // Vec3 * scalar
-      V3 cu = v3(cam.u[0], cam.u[1], cam.u[2]), cv = v3(cam.v[0], cam.v[1], cam.v[2]);
-      V3 offset = cu * rdx + cv * rdy;
-      V3 org = v3(cam.origin[0], cam.origin[1], cam.origin[2]);
-      V3 llc = v3(cam.lower_left_corner[0], cam.lower_left_corner[1], cam.lower_left_corner[2]);
-      V3 hor = v3(cam.horizontal[0], cam.horizontal[1], cam.horizontal[2]);
-      V3 ver = v3(cam.vertical[0], cam.vertical[1], cam.vertical[2]);
-      o = org + offset;
-      d = (((llc + u * hor) + v * ver) - org) - offset;
-      time = rng_urange(rng, cam.shutter_open, cam.shutter_close);
-      att = v3(1, 1, 1);
-      depth = 0;
+      start_sample(L, P.cam, P.nrows, P.ncols);
       need_sample = false;
       ++ray_count;
     }
+    const V3 o = L.o, d = L.d;
+    const double time = L.time;
 
     // ------------------------------------------------------------ A. conservative filter
     const double a = len2(d);  // spheres.nim:30 — also needed by the exact stage
@@ -375,92 +485,25 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_exact_kernel(const 
         sample_done = true;
       } else if (++seg_count, best_t < INF) {
         const tor_hittable* __restrict__ h = exact + best_i;
-        // record fill, spheres.nim:41-46
-        V3 p = o + best_t * d;
-        V3 outward = (p - obj_center(h, time)) * (1.0 / h->radius);
-        bool front_face = dot(d, outward) < 0;  // core.nim:47-49
-        V3 n = front_face ? outward : -outward;
-        const uint32_t mk = h->mat_kind;
-        bool scattered = true;
-        V3 nd;
-        double ntime = 0.0;  // rays.nim:19 default time (Metal / Dielectric)
-        V3 matt = v3(1, 1, 1);
-        if (mk == TOR_LAMBERTIAN) {  // materials.nim:24-30 + sampling.nim:51-55
-          double ang = rng_umax(rng, 6.283185307179586);
-          double z = rng_urange(rng, -1.0, 1.0);
-          double r = sqrt(1.0 - z * z);
-          double sn, cs;
-          detmath::sincos(ang, &sn, &cs);
-          nd = n + v3(r * cs, r * sn, z);
-          ntime = time;
-          matt = v3(h->albedo[0], h->albedo[1], h->albedo[2]);
-        } else if (mk == TOR_METAL) {  // materials.nim:39-47
-          V3 refl = reflect(unit_vector(d), n);
-          V3 s;
-          for (;;) {  // sampling.nim:45-49
-            s.x = rng_urange(rng, -1, 1);
-            s.y = rng_urange(rng, -1, 1);
-            s.z = rng_urange(rng, -1, 1);
-            if (len2(s) < 1.0) break;
-          }
-          nd = refl + h->fuzz_or_ior * s;
-          scattered = dot(nd, n) > 0;
-          matt = v3(h->albedo[0], h->albedo[1], h->albedo[2]);
-        } else {  // materials.nim:62-86
-          double ior = h->fuzz_or_ior;
-          double eta = front_face ? 1.0 / ior : ior;
-          V3 ud = unit_vector(d);
-          double dt = dot(-ud, n);
-          double cos_theta = (dt <= 1.0) ? dt : 1.0;
-          double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
-          bool do_reflect = eta * sin_theta > 1.0;
-          if (!do_reflect) {
-            double r0 = (1 - eta) / (1 + eta);  // schlick, materials.nim:55-60
-            r0 *= r0;
-            double reflect_prob = r0 + (1 - r0) * detmath::pow(1 - cos_theta, 5.0);
-            do_reflect = rng_u01(rng) < reflect_prob;
-          }
-          if (do_reflect) {
-            nd = reflect(ud, n);
-          } else {  // rays.nim:30-37
-            double ct = dot(-ud, n);
-            V3 r_par = eta * (ud + ct * n);
-            V3 r_perp = (-sqrt(1.0 - len2(r_par))) * n;
-            nd = r_par + r_perp;
-          }
-        }
-        if (scattered) {  // render.nim:35-37
-          att.x *= matt.x;
-          att.y *= matt.y;
-          att.z *= matt.z;
-          o = p;
-          d = nd;
-          time = ntime;
-          ++depth;
-          if (depth >= P.max_depth) sample_done = true;  // render.nim:47 -> black
-        } else {
-          sample_done = true;  // render.nim:38 -> black
-        }
-      } else {  // render.nim:40-45
-        V3 ud = unit_vector(d);
-        double t = 0.5 * ud.y + 1.0;
-        color = v3((1.0 - t) + t * 0.5, (1.0 - t) + t * 0.7, (1.0 - t) + t);
-        color.x *= att.x;
-        color.y *= att.y;
-        color.z *= att.z;
+        Surface S;
+        S.center = obj_center(h, time);
+        S.inv_r = 1.0 / h->radius;
+        S.albedo = v3(h->albedo[0], h->albedo[1], h->albedo[2]);
+        S.fuzz_or_ior = h->fuzz_or_ior;
+        S.mat_kind = h->mat_kind;
+        sample_done = shade_hit(L, best_t, S, P.max_depth);
+      } else {
+        color = shade_miss(L);
         sample_done = true;
       }
       if (sample_done) {
-        pix.x += color.x;  // render.nim:67
-        pix.y += color.y;
-        pix.z += color.z;
-        ++sample;
+        L.pix.x += color.x;  // render.nim:67
+        L.pix.y += color.y;
+        L.pix.z += color.z;
+        ++L.sample;
         need_sample = true;
-        if (sample >= P.spp) {  // canvas.nim:47-54
-          double* out = P.pixels + 3ull * px;
-          out[0] = detmath::pow(P.inv_spp * pix.x, P.inv_gamma);
-          out[1] = detmath::pow(P.inv_spp * pix.y, P.inv_gamma);
-          out[2] = detmath::pow(P.inv_spp * pix.z, P.inv_gamma);
+        if (L.sample >= P.spp) {
+          draw_pixel(P.pixels + 3ull * px, L.pix, P.inv_spp, P.inv_gamma);
           need_pixel = true;
           need_sample = false;
           active = false;
