@@ -18,18 +18,20 @@ def _book_cam(tor, aspect=16.0 / 9.0, t0=0.0, t1=1.0):
 
 
 def _check(tor, oracle, ctx, world, cam, h, w, spp, depth=50, gamma=2.2, rows=None):
-    cv = tor.newCanvas(h, w, spp, gamma)
-    cv.pixels[:] = -7.0  # rows that are not selected must stay untouched
-    ctx.render(cv, cam, world, depth, flags=tor.api.TOR_FLAG_COUNT_SEGMENTS, rows=rows)
-    cnt = ctx.counters()
+    """Both closest-hit routes (BVH = default, brute-force scan) against the oracle, bit for bit."""
     ocnt = {}
     ref = np.full((h, w, 3), -7.0)
     oracle.render(h, w, spp, cam.as_array(), world.objects, max_depth=depth, gamma=gamma, rows=rows, math="det",
                   counters=ocnt, out=ref)
-    assert cv.pixels.tobytes() == ref.tobytes(), f"{int((cv.pixels != ref).sum())} float64 values differ"
-    assert cnt["primary_rays"] == ocnt["primary_rays"]
-    if depth > 0:
-        assert cnt["segments"] == ocnt["segments"]
+    for route in (tor.api.TOR_FLAG_BRUTE_FORCE, 0):
+        cv = tor.newCanvas(h, w, spp, gamma)
+        cv.pixels[:] = -7.0  # rows that are not selected must stay untouched
+        ctx.render(cv, cam, world, depth, flags=tor.api.TOR_FLAG_COUNT_SEGMENTS | route, rows=rows)
+        cnt = ctx.counters()
+        assert cv.pixels.tobytes() == ref.tobytes(), f"route {route:#x}: {int((cv.pixels != ref).sum())} float64 values differ"
+        assert cnt["primary_rays"] == ocnt["primary_rays"]
+        if depth > 0:
+            assert cnt["segments"] == ocnt["segments"]
     return cv
 
 

@@ -1,0 +1,18 @@
+"""Developer tool: time the C2 render kernel (device time) for the current env knobs."""
+import os, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import trace_of_radiance_b200 as T
+h, w, spp = (675, 1200, 500) if "--c1" not in sys.argv else (216, 384, 100)
+reps = 3
+ctx = T.Context()
+world = T.random_scene().list()
+cam = T.camera((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 16.0 / 9.0, 0.1, 10.0, 0.0, 1.0)
+fl = T.api.TOR_FLAG_BRUTE_FORCE if "--brute" in sys.argv else 0
+cv = T.newCanvas(h, w, spp, 2.2)
+ms = []
+for _ in range(reps):
+    ctx.render(cv, cam, world, 50, flags=fl)
+    ms.append(ctx.last_kernel_ms())
+print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("TOR_")}, "kernel_ms": ms,
+                  "mray_s": h * w * spp / min(ms) / 1e3}), flush=True)

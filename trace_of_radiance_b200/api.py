@@ -38,11 +38,12 @@ assert HITTABLE_DTYPE.itemsize == 112
 TOR_SPHERE, TOR_MOVING_SPHERE = 0, 1
 TOR_LAMBERTIAN, TOR_METAL, TOR_DIELECTRIC = 0, 1, 2
 TOR_FLAG_COUNT_SEGMENTS = 0x100
+TOR_FLAG_BRUTE_FORCE = 0x200  # scan every object like hittables_lists.nim:48-55 instead of the BVH (same image)
 
 EXPORTED_SYMBOLS = [
     "tor_abi_version", "tor_ctx_create", "tor_ctx_destroy", "tor_last_error", "tor_render", "tor_render_rows",
     "tor_scene_upload", "tor_render_device_async", "tor_sync", "tor_get_counters", "tor_last_kernel_ms",
-    "tor_launch_count", "tor_measure_fp64_peak", "tor_camera_make", "tor_random_scene", "tor_export_ppm", "tor_quantise_rgb8",
+    "tor_launch_count", "tor_measure_fp64_peak", "tor_get_traversal_counters", "tor_scene_info", "tor_camera_make", "tor_random_scene", "tor_export_ppm", "tor_quantise_rgb8",
 ]
 
 
@@ -95,6 +96,8 @@ def load_library():
                                           C.c_int32, C.c_int32, C.c_int32, vp]
     L.tor_sync.argtypes = [vp]
     L.tor_get_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.tor_get_traversal_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.tor_scene_info.argtypes = [vp, C.POINTER(C.c_int64)]
     L.tor_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.tor_launch_count.argtypes = [vp]
     L.tor_launch_count.restype = C.c_int64
@@ -320,7 +323,16 @@ class Context:
     def counters(self):
         out = (C.c_uint64 * 3)()
         self._check(self.L.tor_get_counters(self.h, out))
-        return {"primary_rays": int(out[0]), "segments": int(out[1]), "sphere_tests": int(out[2])}
+        tr = (C.c_uint64 * 2)()
+        self._check(self.L.tor_get_traversal_counters(self.h, tr))
+        return {"primary_rays": int(out[0]), "segments": int(out[1]), "sphere_tests": int(out[2]),
+                "bvh_node_visits": int(tr[0]), "bvh_sphere_tests": int(tr[1])}
+
+    def scene_info(self):
+        out = (C.c_int64 * 6)()
+        self._check(self.L.tor_scene_info(self.h, out))
+        keys = ("objects", "bvh_nodes", "bvh_leaves", "bvh_depth", "objects_outside_tree", "bvh_bytes")
+        return dict(zip(keys, (int(v) for v in out)))
 
     def last_kernel_ms(self):
         ms = C.c_float()

@@ -5,13 +5,16 @@
 // CUDA device every compute entry point fails with TOR_ERR_NO_DEVICE / TOR_ERR_CUDA.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
 #include <vector>
 
 #include "../../include/tor_b200.h"
+#include "tor_bvh.hpp"
 #include "tor_kernels.cuh"
+#include "tor_kernels_bvh.cuh"
 #include "tor_scene_pack.hpp"
 
 namespace {
@@ -22,14 +25,15 @@ struct DeviceState {
   int dev = 0;
   int sm_count = 0;
   int max_smem_optin = 0;
+  int max_smem_per_sm = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  uint8_t* d_blob = nullptr;
+  uint8_t* d_blob = nullptr;  // [brute-force scene blob | BVH blob], each 128-byte aligned
   size_t blob_cap = 0;
   double* d_pixels = nullptr;
   size_t pix_cap = 0;  // bytes
   unsigned long long* d_work = nullptr;      // pixel queue head
-  unsigned long long* d_counters = nullptr;  // [0] primary rays, [1] segments
+  unsigned long long* d_counters = nullptr;  // [0] primary rays, [1] segments, [2] box-pair tests, [3] exact tests
   bool scene_current = false;
   bool timed = false;
 };
@@ -40,10 +44,13 @@ struct tor_ctx {
   std::vector<DeviceState> devs;
   std::string err;
   tor::PackedScene scene;
+  tor::PackedBvh bvh;
+  size_t bvh_off = 0;  // offset of the BVH blob inside the device blob
   tor_camera cam;
   bool have_scene = false;
   int64_t launches = 0;
   uint64_t counters[3] = {0, 0, 0};
+  uint64_t trav_counters[2] = {0, 0};
   bool counters_pending = false;
 };
 
@@ -67,9 +74,15 @@ int fail(tor_ctx* ctx, int code, const std::string& msg) {
   } while (0)
 
 using KernelFn = void (*)(const tor::RenderParams);
+using BvhKernelFn = void (*)(const tor::BvhRenderParams);
 
 struct LaunchPlan {
   KernelFn fn;
+  int stage;
+  size_t smem;
+};
+struct BvhLaunchPlan {
+  BvhKernelFn fn;
   int stage;
   size_t smem;
 };
@@ -83,6 +96,36 @@ LaunchPlan plan_for(const tor::SceneView& sv, int max_smem_optin) {
     return LaunchPlan{tor::render_exact_kernel<kBlock, 1>, 1, sv.hot_bytes + cand};
   return LaunchPlan{tor::render_exact_kernel<kBlock, 0>, 0, cand};
 }
+
+// The hierarchy is staged in shared memory only while two CTAs still fit on an SM (the traversal is
+// latency-bound and wants the warps); beyond that the nodes, then nothing, and L1/L2 serve the rest.
+template <int R>
+BvhLaunchPlan bvh_plan_r(const tor::BvhView& bv, size_t budget) {
+  if (bv.total_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<kBlock, 2, R>, 2, bv.total_bytes};
+  if (bv.nodes_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<kBlock, 1, R>, 1, bv.nodes_bytes};
+  return BvhLaunchPlan{tor::render_bvh_kernel<kBlock, 0, R>, 0, 0};
+}
+
+BvhLaunchPlan bvh_plan_for(const tor::BvhView& bv, int max_smem_per_sm) {
+  const size_t budget = (size_t)max_smem_per_sm / 2 - 2048;
+  // tuning knob (developer use): how many waiting lanes of a warp trigger a shade phase
+  static const int refill = [] {
+    const char* e = getenv("TOR_BVH_REFILL");
+    return e ? atoi(e) : tor::kRefillDefault;
+  }();
+  switch (refill) {
+    case 1: return bvh_plan_r<1>(bv, budget);
+    case 4: return bvh_plan_r<4>(bv, budget);
+    case 8: return bvh_plan_r<8>(bv, budget);
+    case 16: return bvh_plan_r<16>(bv, budget);
+    case 20: return bvh_plan_r<20>(bv, budget);
+    case 24: return bvh_plan_r<24>(bv, budget);
+    case 32: return bvh_plan_r<32>(bv, budget);
+    default: return bvh_plan_r<tor::kRefillDefault>(bv, budget);
+  }
+}
+
+size_t device_blob_bytes(const tor_ctx* ctx) { return ctx->bvh_off + ctx->bvh.blob.size(); }
 
 int ensure_capacity(tor_ctx* ctx, DeviceState& d, size_t blob_bytes, size_t pix_bytes) {
   TOR_CUDA(ctx, cudaSetDevice(d.dev));
@@ -106,11 +149,13 @@ int ensure_capacity(tor_ctx* ctx, DeviceState& d, size_t blob_bytes, size_t pix_
 
 int upload_scene_to(tor_ctx* ctx, DeviceState& d) {
   if (d.scene_current) return TOR_OK;
-  int rc = ensure_capacity(ctx, d, ctx->scene.blob.size(), 0);
+  int rc = ensure_capacity(ctx, d, device_blob_bytes(ctx), 0);
   if (rc) return rc;
   TOR_CUDA(ctx, cudaMemcpyAsync(d.d_blob, ctx->scene.blob.data(), ctx->scene.blob.size(), cudaMemcpyHostToDevice,
                                 d.stream));
-  // the blob vector may be rebuilt by the next tor_scene_upload: finish the copy before returning
+  TOR_CUDA(ctx, cudaMemcpyAsync(d.d_blob + ctx->bvh_off, ctx->bvh.blob.data(), ctx->bvh.blob.size(),
+                                cudaMemcpyHostToDevice, d.stream));
+  // the blob vectors may be rebuilt by the next tor_scene_upload: finish the copies before returning
   TOR_CUDA(ctx, cudaStreamSynchronize(d.stream));
   d.scene_current = true;
   return TOR_OK;
@@ -128,6 +173,16 @@ int set_scene(tor_ctx* ctx, const tor_camera* cam, const void* objects, int64_t 
     ctx->have_scene = false;
     return fail(ctx, TOR_ERR_INVALID_ARG, err);
   }
+  {
+    std::vector<tor_hittable> objs((size_t)len);
+    for (int64_t i = 0; i < len; ++i)
+      tor::decode_object((const uint8_t*)objects + i * stride, stride, &objs[(size_t)i]);  // validated by pack_scene
+    if (!tor::pack_bvh(objs, *cam, &ctx->bvh, &err)) {
+      ctx->have_scene = false;
+      return fail(ctx, TOR_ERR_INVALID_ARG, err);
+    }
+  }
+  ctx->bvh_off = (ctx->scene.blob.size() + 127) / 128 * 128;
   ctx->cam = *cam;
   ctx->have_scene = true;
   for (DeviceState& d : ctx->devs) d.scene_current = false;
@@ -153,46 +208,78 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
   if (nsel == 0) return TOR_OK;
   TOR_CUDA(ctx, cudaSetDevice(d.dev));
 
-  tor::RenderParams P;
-  memset(&P, 0, sizeof(P));
-  P.sv = ctx->scene.view;
-  P.blob = d.d_blob;
-  P.cam = ctx->cam;
-  P.pixels = d_out;
-  P.nrows = nrows;
-  P.ncols = ncols;
-  P.spp = spp;
-  P.max_depth = (int32_t)max_depth;
-  P.inv_spp = 1.0 / (double)spp;             // canvas.nim:49
-  P.inv_gamma = 1.0 / (double)gamma;         // canvas.nim:50 — float32 widened to float64
-  P.row_begin = row_begin;
-  P.row_step = row_step;
-  P.nsel_rows = nsel;
-  P.count_segments = (flags & TOR_FLAG_COUNT_SEGMENTS) ? 1u : 0u;
-  P.work_counter = d.d_work;
-  P.counters = d.d_counters;
-
-  LaunchPlan plan = plan_for(P.sv, d.max_smem_optin);
-  TOR_CUDA(ctx, cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-  int per_sm = 0;
-  TOR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, kBlock, plan.smem));
-  if (per_sm < 1) return fail(ctx, TOR_ERR_CUDA, "render kernel does not fit on an SM");
-  // persistent lanes: one grid that exactly fills the GPU; lanes pull pixels from d_work
-  unsigned long long total_px = (unsigned long long)nsel * (unsigned long long)ncols;
-  unsigned long long want = (total_px + kBlock - 1) / kBlock;
-  unsigned long long cap = (unsigned long long)d.sm_count * (unsigned long long)per_sm;
-  int grid = (int)(want < cap ? want : cap);
-
+  const bool count = (flags & TOR_FLAG_COUNT_SEGMENTS) != 0;
+  const unsigned long long total_px = (unsigned long long)nsel * (unsigned long long)ncols;
+  const unsigned long long want = (total_px + kBlock - 1) / kBlock;
   TOR_CUDA(ctx, cudaMemsetAsync(d.d_work, 0, sizeof(unsigned long long), stream));
-  if (timed) TOR_CUDA(ctx, cudaEventRecord(d.ev0, stream));
-  plan.fn<<<grid, kBlock, plan.smem, stream>>>(P);
+
+  if (flags & TOR_FLAG_BRUTE_FORCE) {
+    tor::RenderParams P;
+    memset(&P, 0, sizeof(P));
+    P.sv = ctx->scene.view;
+    P.blob = d.d_blob;
+    P.cam = ctx->cam;
+    P.pixels = d_out;
+    P.nrows = nrows;
+    P.ncols = ncols;
+    P.spp = spp;
+    P.max_depth = (int32_t)max_depth;
+    P.inv_spp = 1.0 / (double)spp;      // canvas.nim:49
+    P.inv_gamma = 1.0 / (double)gamma;  // canvas.nim:50 — float32 widened to float64
+    P.row_begin = row_begin;
+    P.row_step = row_step;
+    P.nsel_rows = nsel;
+    P.count_segments = count ? 1u : 0u;
+    P.work_counter = d.d_work;
+    P.counters = d.d_counters;
+
+    LaunchPlan plan = plan_for(P.sv, d.max_smem_optin);
+    TOR_CUDA(ctx, cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    int per_sm = 0;
+    TOR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, kBlock, plan.smem));
+    if (per_sm < 1) return fail(ctx, TOR_ERR_CUDA, "render kernel does not fit on an SM");
+    // persistent lanes: one grid that exactly fills the GPU; lanes pull pixels from d_work
+    unsigned long long cap = (unsigned long long)d.sm_count * (unsigned long long)per_sm;
+    int grid = (int)(want < cap ? want : cap);
+    if (timed) TOR_CUDA(ctx, cudaEventRecord(d.ev0, stream));
+    plan.fn<<<grid, kBlock, plan.smem, stream>>>(P);
+  } else {
+    tor::BvhRenderParams P;
+    memset(&P, 0, sizeof(P));
+    P.bv = ctx->bvh.view;
+    P.blob = d.d_blob + ctx->bvh_off;
+    P.cam = ctx->cam;
+    P.pixels = d_out;
+    P.nrows = nrows;
+    P.ncols = ncols;
+    P.spp = spp;
+    P.max_depth = (int32_t)max_depth;
+    P.inv_spp = 1.0 / (double)spp;
+    P.inv_gamma = 1.0 / (double)gamma;
+    P.row_begin = row_begin;
+    P.row_step = row_step;
+    P.nsel_rows = nsel;
+    P.count_segments = count ? 1u : 0u;
+    P.work_counter = d.d_work;
+    P.counters = d.d_counters;
+
+    BvhLaunchPlan plan = bvh_plan_for(P.bv, d.max_smem_per_sm);
+    TOR_CUDA(ctx, cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    int per_sm = 0;
+    TOR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, kBlock, plan.smem));
+    if (per_sm < 1) return fail(ctx, TOR_ERR_CUDA, "render kernel does not fit on an SM");
+    unsigned long long cap = (unsigned long long)d.sm_count * (unsigned long long)per_sm;
+    int grid = (int)(want < cap ? want : cap);
+    if (timed) TOR_CUDA(ctx, cudaEventRecord(d.ev0, stream));
+    plan.fn<<<grid, kBlock, plan.smem, stream>>>(P);
+  }
   TOR_CUDA(ctx, cudaGetLastError());
   if (timed) {
     TOR_CUDA(ctx, cudaEventRecord(d.ev1, stream));
     d.timed = true;
   }
   ctx->launches += 1;
-  if (P.count_segments) ctx->counters_pending = true;
+  if (count) ctx->counters_pending = true;
   return TOR_OK;
 }
 
@@ -239,11 +326,12 @@ int tor_ctx_create(const int* devices, int ndev, tor_ctx** out) {
     }
     d.sm_count = prop.multiProcessorCount;
     d.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    d.max_smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     bool ok = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&d.ev0) == cudaSuccess && cudaEventCreate(&d.ev1) == cudaSuccess &&
               cudaMalloc(&d.d_work, sizeof(unsigned long long)) == cudaSuccess &&
-              cudaMalloc(&d.d_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
-              cudaMemset(d.d_counters, 0, 2 * sizeof(unsigned long long)) == cudaSuccess;
+              cudaMalloc(&d.d_counters, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMemset(d.d_counters, 0, 4 * sizeof(unsigned long long)) == cudaSuccess;
     ctx->devs.push_back(d);
     if (!ok) {
       g_create_err = std::string("context allocation: ") + cudaGetErrorString(cudaGetLastError());
@@ -332,7 +420,7 @@ int tor_render_rows(tor_ctx* ctx, tor_canvas* canvas, const tor_camera* cam, con
     const int32_t rb = row_begin + g * row_step;
     const int32_t rs = row_step * ndev;
     const int32_t nsel = (row_end - rb + rs - 1) / rs;
-    rc = ensure_capacity(ctx, d, ctx->scene.blob.size(), (size_t)nsel * row_bytes);
+    rc = ensure_capacity(ctx, d, device_blob_bytes(ctx), (size_t)nsel * row_bytes);
     if (rc) return rc;
     rc = upload_scene_to(ctx, d);
     if (rc) return rc;
@@ -356,20 +444,43 @@ int tor_render(tor_ctx* ctx, tor_canvas* canvas, const tor_camera* cam, const vo
 
 int tor_get_counters(tor_ctx* ctx, uint64_t out[3]) {
   if (!ctx || !out) return TOR_ERR_INVALID_ARG;
-  uint64_t rays = 0, segs = 0;
+  uint64_t rays = 0, segs = 0, boxes = 0, tests = 0;
   for (DeviceState& d : ctx->devs) {
-    unsigned long long h[2] = {0, 0};
+    unsigned long long h[4] = {0, 0, 0, 0};
     TOR_CUDA(ctx, cudaSetDevice(d.dev));
     TOR_CUDA(ctx, cudaStreamSynchronize(d.stream));
     TOR_CUDA(ctx, cudaMemcpy(h, d.d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     TOR_CUDA(ctx, cudaMemset(d.d_counters, 0, sizeof(h)));
     rays += h[0];
     segs += h[1];
+    boxes += h[2];
+    tests += h[3];
   }
   out[0] = rays;
   out[1] = segs;
   out[2] = segs * (uint64_t)(ctx->have_scene ? ctx->scene.view.n_objects : 0);
+  ctx->trav_counters[0] = boxes;
+  ctx->trav_counters[1] = tests;
   ctx->counters_pending = false;
+  return TOR_OK;
+}
+
+int tor_get_traversal_counters(tor_ctx* ctx, uint64_t out[2]) {
+  if (!ctx || !out) return TOR_ERR_INVALID_ARG;
+  out[0] = ctx->trav_counters[0];
+  out[1] = ctx->trav_counters[1];
+  return TOR_OK;
+}
+
+int tor_scene_info(tor_ctx* ctx, int64_t out[6]) {
+  if (!ctx || !out) return TOR_ERR_INVALID_ARG;
+  if (!ctx->have_scene) return fail(ctx, TOR_ERR_INVALID_ARG, "no scene has been set on this context");
+  out[0] = ctx->scene.view.n_objects;
+  out[1] = ctx->bvh.view.n_nodes;
+  out[2] = ctx->bvh.n_leaves;
+  out[3] = ctx->bvh.max_depth;
+  out[4] = ctx->bvh.view.n_objects - ctx->bvh.view.n_tree_objs;
+  out[5] = (int64_t)ctx->bvh.blob.size();
   return TOR_OK;
 }
 

@@ -44,19 +44,22 @@ static_assert(sizeof(BvhNode) == 64, "BvhNode layout");
 // the reference performs on the same inputs (so precomputing them changes no bit):
 //   dc = center1 - center0 (moving_spheres.nim:43), r2 = radius*radius (spheres.nim:32),
 //   inv_r = 1.0/radius (spheres.nim:43 through vec3s.nim:93-94).
-struct alignas(16) ObjRec {  // 128 bytes
+struct alignas(16) ObjRec {  // 128 bytes; the hit test of a static sphere reads only the first 48
   double c0[3];
-  double r2m;  // filter: r^2 inflated by the conservative slack (tor_scene_pack.hpp)
-  double dc[3];
   double r2;
-  double t0, t1;  // time0, time1 (static spheres: 0, 1 and dc = 0)
-  double albedo[3];
-  double fuzz_or_ior;
-  double inv_r;
   uint32_t kind_mat;  // kind | mat_kind << 8
   uint32_t orig;      // index in the caller's HittableList (ties go to the lowest, hittables_lists.nim:48-55)
+  double inv_r;
+  double dc[3];
+  double pad;
+  double t0, t1;  // time0, time1 (movers only)
+  double albedo[3];
+  double fuzz_or_ior;
 };
 static_assert(sizeof(ObjRec) == 128, "ObjRec layout");
+// kind_mat flag: a mover with time0 == +0.0 and time1 == 1.0, whose lerp parameter
+// (time - time0) / (time1 - time0) (moving_spheres.nim:41-42) is exactly `time` in IEEE arithmetic
+static constexpr uint32_t kObjUnitInterval = 1u << 16;
 
 struct BvhView {  // kernel parameter
   int32_t n_nodes;
@@ -66,6 +69,8 @@ struct BvhView {  // kernel parameter
   uint32_t off_nodes, off_objs;
   uint32_t nodes_bytes;   // blob prefix holding the nodes
   uint32_t total_bytes;
+  float s_limit;          // ray origins with a larger |coordinate| take the "test everything" route
+  int32_t max_depth;
 };
 
 struct PackedBvh {
@@ -366,8 +371,6 @@ static inline bool pack_bvh(const std::vector<tor_hittable>& objs, const tor_cam
   const int n_tree = (int)order.size();
   for (int i : always) order.push_back(i);
 
-  // time range for the filter slack (same bound as the brute-force filter, tor_scene_pack.hpp)
-  const double K = kFilterSlack;
   std::vector<ObjRec> recs((size_t)n);
   for (int j = 0; j < n; ++j) {
     const tor_hittable& h = objs[(size_t)order[(size_t)j]];
@@ -381,20 +384,12 @@ static inline bool pack_bvh(const std::vector<tor_hittable>& objs, const tor_cam
     }
     r.r2 = h.radius * h.radius;  // spheres.nim:32
     r.inv_r = 1.0 / h.radius;    // vec3s.nim:93-94
-    r.t0 = mover ? h.time0 : 0.0;
-    r.t1 = mover ? h.time1 : 1.0;
+    r.t0 = h.time0;
+    r.t1 = h.time1;
     r.fuzz_or_ior = h.fuzz_or_ior;
     r.kind_mat = h.kind | (h.mat_kind << 8);
+    if (mover && h.time0 == 0.0 && !signbit(h.time0) && h.time1 == 1.0) r.kind_mat |= kObjUnitInterval;
     r.orig = (uint32_t)order[(size_t)j];
-    double ccmax;
-    if (mover) {
-      ccmax = mover_cc_bound(h, time_lo, time_hi);
-    } else {
-      ccmax = h.center0[0] * h.center0[0] + h.center0[1] * h.center0[1] + h.center0[2] * h.center0[2];
-    }
-    double r2m = r.r2 + K * (ccmax + r.r2);
-    if (!(r2m < INFINITY)) r2m = INFINITY;  // NaN / inf: the filter always passes, the exact test decides
-    r.r2m = r2m;
   }
 
   BvhView& v = out->view;
@@ -406,6 +401,8 @@ static inline bool pack_bvh(const std::vector<tor_hittable>& objs, const tor_cam
   v.nodes_bytes = (uint32_t)(nodes.size() * sizeof(BvhNode));
   v.off_objs = v.nodes_bytes;
   v.total_bytes = v.off_objs + (uint32_t)(recs.size() * sizeof(ObjRec));
+  v.s_limit = bvh_detail::f32_down(1.001 * S);  // the padding was sized for origins within S (see header)
+  v.max_depth = B.max_depth;
   out->blob.assign(v.total_bytes, 0);
   memcpy(out->blob.data() + v.off_nodes, nodes.data(), v.nodes_bytes);
   memcpy(out->blob.data() + v.off_objs, recs.data(), recs.size() * sizeof(ObjRec));

@@ -1,0 +1,368 @@
+// tor_kernels_bvh.cuh — the sm_100a render kernel with a bounding-volume hierarchy in front of the
+// reference's sphere test (exact mode; the image is bit-identical to the brute-force scan).
+//
+// Why the result cannot change: the in-order scan of hittables_lists.nim:48-55 returns
+//     argmin over objects of (t_i, i),   t_i = the object's first root in (t_min, +inf)
+// (see exact_first_root in tor_kernels.cuh).  The hierarchy (tor_bvh.hpp) is only a conservative
+// *filter*: a subtree is skipped when the ray misses its padded float32 box or enters it beyond the
+// closest root found so far; every object that survives is evaluated with the reference's own
+// non-fused float64 arithmetic, and ties go to the lowest original index.
+//
+// Execution model: persistent lanes, one pixel stream per lane (the reference shares one RNG stream
+// across a pixel's samples, render.nim:59-67).  The kernel alternates two phases:
+//   S  "shade": lanes whose traversal has finished shade the hit / the sky, start the next segment,
+//      sample or pixel (pixels come from a global atomic queue) and set up the next traversal;
+//   T  "traverse": while-while traversal (inner nodes until a leaf, then the leaf's spheres), which
+//      keeps running until at least kRefill lanes of the warp wait for phase S (or nobody traverses).
+// A lane keeps its traversal state (node, stack, closest hit) across phase S of its neighbours, so the
+// expensive float64 shading code (sincos, sqrt, divides) always runs with many lanes, and the
+// traversal loop always with at least 32 - kRefill.
+#pragma once
+#include "tor_bvh.hpp"
+#include "tor_kernels.cuh"
+
+namespace tor {
+
+struct BvhRenderParams {
+  BvhView bv;
+  const uint8_t* blob;  // device copy of PackedBvh::blob
+  tor_camera cam;
+  double* pixels;
+  int32_t nrows, ncols, spp;
+  int32_t max_depth;
+  double inv_spp, inv_gamma;
+  int32_t row_begin, row_step, nsel_rows;
+  uint32_t count_segments;
+  unsigned long long* work_counter;
+  unsigned long long* counters;  // [0] primary rays, [1] segments, [2] box-pair tests, [3] exact sphere tests
+};
+
+static constexpr int kRefillDefault = 12;
+
+// One object of a leaf (or of the "always" list) against the ray: the reference's arithmetic
+// (spheres.nim:28-49 / moving_spheres.nim:39-67), operation for operation.  r2 = radius*radius and
+// dc = center1 - center0 were computed on the host with the same IEEE operations.
+struct QCache {  // lerp parameter of moving_spheres.nim:41-42, one divide per (time0, time1) per segment
+  double t0, t1, q;
+};
+
+__device__ __forceinline__ V3 rec_center(const double2* __restrict__ r, uint32_t kind_mat, double time, QCache& qc) {
+  double2 a0 = r[0], a1 = r[1];
+  V3 c0 = v3(a0.x, a0.y, a1.x);
+  if ((kind_mat & 0xffu) == TOR_MOVING_SPHERE) {
+    double2 a3 = r[3], a4 = r[4];
+    double q;
+    if (kind_mat & kObjUnitInterval) {
+      // time0 = +0.0, time1 = 1.0: (time - 0.0) / (1.0 - 0.0) is `time` itself, bit for bit
+      q = time;
+    } else {
+      double2 a5 = r[5];
+      if (!(a5.x == qc.t0 && a5.y == qc.t1)) {
+        qc.t0 = a5.x;
+        qc.t1 = a5.y;
+        qc.q = (time - a5.x) / (a5.y - a5.x);
+      }
+      q = qc.q;
+    }
+    return c0 + (q * v3(a3.x, a3.y, a4.x));
+  }
+  return c0;
+}
+
+template <int BLOCK, int STAGE, int REFILL>
+__global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __grid_constant__ BvhRenderParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t stage_bar;
+
+  const int tid = threadIdx.x;
+  const BvhView& bv = P.bv;
+  const uint32_t staged_bytes = STAGE == 2 ? bv.total_bytes : (STAGE == 1 ? bv.nodes_bytes : 0u);
+
+  if (tid == 0) {
+    mbar_init(&stage_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (staged_bytes) {
+    if (tid == 0) {
+      mbar_expect_tx(&stage_bar, staged_bytes);
+      const uint32_t kChunk = 32768;
+      for (uint32_t off = 0; off < staged_bytes; off += kChunk) {
+        uint32_t n = staged_bytes - off < kChunk ? staged_bytes - off : kChunk;
+        tma_bulk_g2s(smem + off, P.blob + off, n, &stage_bar);
+      }
+    }
+    mbar_wait(&stage_bar, 0);
+  }
+  const float4* __restrict__ nodes = reinterpret_cast<const float4*>((STAGE >= 1 ? smem : P.blob) + bv.off_nodes);
+  const double2* __restrict__ recs = reinterpret_cast<const double2*>((STAGE == 2 ? smem : P.blob) + bv.off_objs);
+
+  const double INF = __longlong_as_double(0x7ff0000000000000ll);
+  const double t_min = 0.001;  // render.nim:28
+  const unsigned long long total_px = (unsigned long long)P.nsel_rows * (unsigned long long)P.ncols;
+
+  Lane L;
+  L.pix = v3(0, 0, 0);
+  L.att = v3(1, 1, 1);
+  L.o = v3(0, 0, 0);
+  L.d = v3(0, 0, 1);
+  L.time = 0.0;
+  L.row = L.col = L.sample = L.depth = 0;
+  unsigned long long px = 0;
+  bool active = false, need_pixel = true, need_sample = false;
+  bool trav_done = false;  // the current segment's closest hit is final
+  bool need_setup = false;  // a new segment needs its traversal state
+  unsigned long long seg_count = 0, ray_count = 0, box_count = 0, test_count = 0;
+
+  // traversal state
+  int32_t stk[kBvhStackDepth];
+  float stk_t[kBvhStackDepth];
+  int sp = 0;
+  int32_t cur = 0;
+  float idx = 0.f, idy = 0.f, idz = 0.f, oix = 0.f, oiy = 0.f, oiz = 0.f;  // 1/d and o/d in float32
+  double a = 1.0;       // d.d  (spheres.nim:30)
+  double best_t = INF;  // closest root so far
+  float best_f = 0.f;   // the same rounded up to float32
+  uint32_t best_orig = 0xffffffffu;
+  int32_t best_rec = -1;
+  QCache qc;
+  qc.t0 = qc.t1 = qc.q = 0.0;
+
+  auto test_rec = [&](int32_t ri) {
+    const double2* __restrict__ r = recs + 8 * ri;
+    const double2 a1 = r[1], a2 = r[2];
+    const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
+    const uint32_t orig = (uint32_t)((unsigned long long)__double_as_longlong(a2.x) >> 32);
+    const V3 o = L.o, d = L.d;
+    V3 oc = o - rec_center(r, kind_mat, L.time, qc);
+    double half_b = dot(oc, d);
+    double c = len2(oc) - a1.y;
+    double disc = half_b * half_b - a * c;
+    if (disc > 0) {
+      double root = sqrt(disc);
+      double t = INF;
+      double sol = (-half_b - root) / a;
+      if (t_min < sol) {
+        t = sol;
+      } else {
+        sol = (-half_b + root) / a;
+        if (t_min < sol) t = sol;
+      }
+      if (t < best_t || (t == best_t && orig < best_orig && t < INF)) {
+        best_t = t;
+        best_orig = orig;
+        best_rec = ri;
+        best_f = __double2float_ru(t);
+      }
+    }
+  };
+
+  for (;;) {
+    // =================================================================== phase S
+    if (active && trav_done) {
+      trav_done = false;
+      bool sample_done;
+      V3 color = v3(0, 0, 0);
+      if (P.max_depth <= 0) {  // render.nim:25 — the bounce loop body never runs
+        sample_done = true;
+      } else if (++seg_count, best_rec >= 0) {
+        const double2* __restrict__ r = recs + 8 * best_rec;
+        const double2 a2 = r[2], a6 = r[6], a7 = r[7];
+        const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
+        Surface S;
+        S.center = rec_center(r, kind_mat, L.time, qc);  // moving_spheres.nim:61
+        S.inv_r = a2.y;
+        S.albedo = v3(a6.x, a6.y, a7.x);
+        S.fuzz_or_ior = a7.y;
+        S.mat_kind = (kind_mat >> 8) & 0xffu;
+        sample_done = shade_hit(L, best_t, S, P.max_depth);
+      } else {
+        color = shade_miss(L);
+        sample_done = true;
+      }
+      need_setup = !sample_done;
+      if (sample_done) {
+        L.pix.x += color.x;  // render.nim:67
+        L.pix.y += color.y;
+        L.pix.z += color.z;
+        ++L.sample;
+        need_sample = true;
+        if (L.sample >= P.spp) {
+          draw_pixel(P.pixels + 3ull * px, L.pix, P.inv_spp, P.inv_gamma);
+          need_pixel = true;
+          need_sample = false;
+          active = false;
+        }
+      }
+    }
+    __syncwarp();
+    if (need_pixel) {
+      need_pixel = false;
+      active = false;
+      for (;;) {
+        px = atomicAdd(P.work_counter, 1ull);
+        if (px >= total_px) break;
+        if (P.spp > 0) {
+          int32_t ri = (int32_t)(px / (unsigned long long)P.ncols);
+          L.col = (int32_t)(px - (unsigned long long)ri * (unsigned long long)P.ncols);
+          L.row = P.row_begin + ri * P.row_step;
+          rng_seed_pixel(L.rng, L.row, L.col);  // render.nim:59-60
+          L.pix = v3(0, 0, 0);
+          L.sample = 0;
+          active = true;
+          need_sample = true;
+          break;
+        }
+        double* out = P.pixels + 3ull * px;  // no samples: draw() of the zero colour (canvas.nim:49-54)
+        out[0] = out[1] = out[2] = detmath::pow(P.inv_spp * 0.0, P.inv_gamma);
+      }
+    }
+    if (!__any_sync(0xffffffffu, active)) break;
+
+    if (active && need_sample) {
+      start_sample(L, P.cam, P.nrows, P.ncols);
+      need_sample = false;
+      need_setup = true;
+      ++ray_count;
+    }
+    __syncwarp();
+    if (active && need_setup) {
+      need_setup = false;
+      best_t = INF;
+      best_orig = 0xffffffffu;
+      best_rec = -1;
+      best_f = __int_as_float(0x7f800000);
+      qc.t0 = qc.t1 = __longlong_as_double(0x7ff8000000000000ll);  // NaN: never equal, forces the first divide
+      if (P.max_depth <= 0) {
+        trav_done = true;
+      } else {
+        const V3 o = L.o, d = L.d;
+        a = len2(d);
+        // float32 ray for the slab tests.  Components of d far below the largest one are replaced by
+        // +-2^-60 * dmax (a direction change below 2^-60, negligible against the box padding) so that 1/d
+        // stays finite; rays outside the range the padding was derived for test everything instead.
+        float dxf = __double2float_rn(d.x), dyf = __double2float_rn(d.y), dzf = __double2float_rn(d.z);
+        float oxf = __double2float_rn(o.x), oyf = __double2float_rn(o.y), ozf = __double2float_rn(o.z);
+        float dmax = fmaxf(fabsf(dxf), fmaxf(fabsf(dyf), fabsf(dzf)));
+        float omax = fmaxf(fabsf(oxf), fmaxf(fabsf(oyf), fabsf(ozf)));
+        bool ok = dmax >= 0x1p-40f && dmax <= 0x1p40f && omax <= bv.s_limit;
+        ok = ok && dxf == dxf && dyf == dyf && dzf == dzf && oxf == oxf && oyf == oyf && ozf == ozf;
+        if (ok) {
+          float dmin = dmax * 0x1p-60f;
+          if (fabsf(dxf) < dmin) dxf = copysignf(dmin, dxf);
+          if (fabsf(dyf) < dmin) dyf = copysignf(dmin, dyf);
+          if (fabsf(dzf) < dmin) dzf = copysignf(dmin, dzf);
+          idx = __frcp_rn(dxf);
+          idy = __frcp_rn(dyf);
+          idz = __frcp_rn(dzf);
+          oix = oxf * idx;
+          oiy = oyf * idy;
+          oiz = ozf * idz;
+        } else {
+          idx = idy = idz = 0.f;  // every slab interval becomes [0, 0]: all boxes pass
+          oix = oiy = oiz = 0.f;
+        }
+        for (int32_t ri = bv.n_tree_objs; ri < bv.n_objects; ++ri) {  // objects without a finite box
+          test_rec(ri);
+          ++test_count;
+        }
+        cur = 0;
+        sp = 0;
+      }
+    }
+
+    // =================================================================== phase T
+    __syncwarp();
+    for (;;) {
+      const bool trav = active && !trav_done;
+      const int n_trav = __popc(__ballot_sync(0xffffffffu, trav));
+      if (n_trav == 0) break;
+      const int n_wait = __popc(__ballot_sync(0xffffffffu, active && trav_done));
+      if (n_wait >= REFILL) break;
+      // ---- inner nodes until a leaf (cur < 0) or the end of the traversal
+      if (trav) {
+        while (cur >= 0) {
+          const float4* __restrict__ nd = nodes + 4 * cur;
+          const float4 n0 = nd[0], n1 = nd[1], n2 = nd[2];
+          const int4 n3 = *reinterpret_cast<const int4*>(nd + 3);
+          ++box_count;
+          // child 0: lo = (n0.x, n0.y, n0.z), hi = (n0.w, n1.x, n1.y); child 1: lo = (n1.z, n1.w, n2.x), hi = (n2.y, n2.z, n2.w)
+          float ax0 = fmaf(n0.x, idx, -oix), ax1 = fmaf(n0.w, idx, -oix);
+          float ay0 = fmaf(n0.y, idy, -oiy), ay1 = fmaf(n1.x, idy, -oiy);
+          float az0 = fmaf(n0.z, idz, -oiz), az1 = fmaf(n1.y, idz, -oiz);
+          float near0 = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.f));
+          float far0 = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), best_f));
+          float bx0 = fmaf(n1.z, idx, -oix), bx1 = fmaf(n2.y, idx, -oix);
+          float by0 = fmaf(n1.w, idy, -oiy), by1 = fmaf(n2.z, idy, -oiy);
+          float bz0 = fmaf(n2.x, idz, -oiz), bz1 = fmaf(n2.w, idz, -oiz);
+          float near1 = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), 0.f));
+          float far1 = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), best_f));
+          const bool h0 = near0 <= far0, h1 = near1 <= far1;
+          if (h0 && h1) {
+            const bool first0 = near0 <= near1;
+            stk[sp] = first0 ? n3.y : n3.x;
+            stk_t[sp] = first0 ? near1 : near0;
+            ++sp;
+            cur = first0 ? n3.x : n3.y;
+          } else if (h0 || h1) {
+            cur = h0 ? n3.x : n3.y;
+          } else {
+            // pop: skip subtrees that start beyond the closest root found since they were pushed
+            cur = -1;
+            trav_done = true;
+            while (sp > 0) {
+              --sp;
+              if (stk_t[sp] <= best_f) {
+                cur = stk[sp];
+                trav_done = false;
+                break;
+              }
+            }
+            if (trav_done) break;
+          }
+        }
+      }
+      __syncwarp();
+      // ---- leaves: the reference's sphere test on each object, all lanes that hold a leaf in step
+      const bool leaf = trav && !trav_done;
+      const int32_t lv = ~cur;
+      const int32_t first = lv >> 4;
+      const int32_t cnt = leaf ? (lv & 15) : 0;
+      const int32_t max_cnt = __reduce_max_sync(0xffffffffu, cnt);
+      for (int32_t k = 0; k < max_cnt; ++k) {
+        if (k < cnt) test_rec(first + k);
+        __syncwarp();
+      }
+      if (leaf) {
+        test_count += cnt;
+        trav_done = true;
+        while (sp > 0) {
+          --sp;
+          if (stk_t[sp] <= best_f) {
+            cur = stk[sp];
+            trav_done = false;
+            break;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  if (P.count_segments) {
+    for (int ofs = 16; ofs > 0; ofs >>= 1) {
+      seg_count += __shfl_down_sync(0xffffffffu, seg_count, ofs);
+      ray_count += __shfl_down_sync(0xffffffffu, ray_count, ofs);
+      box_count += __shfl_down_sync(0xffffffffu, box_count, ofs);
+      test_count += __shfl_down_sync(0xffffffffu, test_count, ofs);
+    }
+    if ((tid & 31) == 0) {
+      atomicAdd(P.counters + 0, ray_count);
+      atomicAdd(P.counters + 1, seg_count);
+      atomicAdd(P.counters + 2, box_count);
+      atomicAdd(P.counters + 3, test_count);
+    }
+  }
+}
+
+}  // namespace tor
