@@ -5,6 +5,9 @@ sys.path.insert(0, ROOT)
 import trace_of_radiance_b200 as T
 h, w, spp = (675, 1200, 500) if "--c1" not in sys.argv else (216, 384, 100)
 reps = 3
+if "--dims" in sys.argv:
+    i = sys.argv.index("--dims")
+    h, w, spp, reps = (int(x) for x in sys.argv[i + 1:i + 5])
 ctx = T.Context()
 world = T.random_scene().list()
 cam = T.camera((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 16.0 / 9.0, 0.1, 10.0, 0.0, 1.0)

@@ -99,30 +99,22 @@ LaunchPlan plan_for(const tor::SceneView& sv, int max_smem_optin) {
 
 // The hierarchy is staged in shared memory only while two CTAs still fit on an SM (the traversal is
 // latency-bound and wants the warps); beyond that the nodes, then nothing, and L1/L2 serve the rest.
-template <int R>
-BvhLaunchPlan bvh_plan_r(const tor::BvhView& bv, size_t budget) {
-  if (bv.total_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<kBlock, 2, R>, 2, bv.total_bytes};
-  if (bv.nodes_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<kBlock, 1, R>, 1, bv.nodes_bytes};
-  return BvhLaunchPlan{tor::render_bvh_kernel<kBlock, 0, R>, 0, 0};
-}
-
 BvhLaunchPlan bvh_plan_for(const tor::BvhView& bv, int max_smem_per_sm) {
   const size_t budget = (size_t)max_smem_per_sm / 2 - 2048;
-  // tuning knob (developer use): how many waiting lanes of a warp trigger a shade phase
-  static const int refill = [] {
+  if (bv.total_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<kBlock, 2>, 2, bv.total_bytes};
+  if (bv.nodes_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<kBlock, 1>, 1, bv.nodes_bytes};
+  return BvhLaunchPlan{tor::render_bvh_kernel<kBlock, 0>, 0, 0};
+}
+
+// kRefill of the BVH kernel (tor_kernels_bvh.cuh).  The environment variable is a developer tuning knob;
+// the default is the measured optimum on B200 for C2.
+int bvh_refill() {
+  static const int v = [] {
     const char* e = getenv("TOR_BVH_REFILL");
-    return e ? atoi(e) : tor::kRefillDefault;
+    int r = e ? atoi(e) : 20;
+    return r < 1 ? 1 : (r > 32 ? 32 : r);
   }();
-  switch (refill) {
-    case 1: return bvh_plan_r<1>(bv, budget);
-    case 4: return bvh_plan_r<4>(bv, budget);
-    case 8: return bvh_plan_r<8>(bv, budget);
-    case 16: return bvh_plan_r<16>(bv, budget);
-    case 20: return bvh_plan_r<20>(bv, budget);
-    case 24: return bvh_plan_r<24>(bv, budget);
-    case 32: return bvh_plan_r<32>(bv, budget);
-    default: return bvh_plan_r<tor::kRefillDefault>(bv, budget);
-  }
+  return v;
 }
 
 size_t device_blob_bytes(const tor_ctx* ctx) { return ctx->bvh_off + ctx->bvh.blob.size(); }
@@ -262,6 +254,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     P.count_segments = count ? 1u : 0u;
     P.work_counter = d.d_work;
     P.counters = d.d_counters;
+    P.refill = bvh_refill();
 
     BvhLaunchPlan plan = bvh_plan_for(P.bv, d.max_smem_per_sm);
     TOR_CUDA(ctx, cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
@@ -272,6 +265,11 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     int grid = (int)(want < cap ? want : cap);
     if (timed) TOR_CUDA(ctx, cudaEventRecord(d.ev0, stream));
     plan.fn<<<grid, kBlock, plan.smem, stream>>>(P);
+    TOR_CUDA(ctx, cudaGetLastError());
+    // canvas.nim:47-54 `draw` over the sums the render kernel left behind
+    const unsigned long long nch = total_px * 3ull;
+    tor::draw_kernel<<<(unsigned)((nch + 255) / 256), 256, 0, stream>>>(d_out, nch, P.inv_spp, P.inv_gamma);
+    ctx->launches += 1;
   }
   TOR_CUDA(ctx, cudaGetLastError());
   if (timed) {

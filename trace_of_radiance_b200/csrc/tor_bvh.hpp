@@ -340,6 +340,24 @@ static inline bool pack_bvh(const std::vector<tor_hittable>& objs, const tor_cam
     prims.push_back(p);
   }
 
+  // Objects whose box spans most of the scene (the r = 1000 ground sphere of scenes.nim:15) prune nothing from
+  // inside the tree.  They join the "always" list instead: tested first, on every segment, by all lanes of the
+  // warp together, and their root bounds the traversal before it starts.
+  if (prims.size() > 4) {
+    Box all;
+    box_reset(all);
+    for (const Prim& p : prims) box_grow(all, p.b);
+    const double limit = 0.5 * box_area(all);
+    std::vector<Prim> kept;
+    for (const Prim& p : prims) {
+      if (always.size() < 8 && box_area(p.b) > limit)
+        always.push_back(p.obj);
+      else
+        kept.push_back(p);
+    }
+    prims.swap(kept);
+  }
+
   std::vector<BvhNode> nodes;
   std::vector<int> order;
   Builder B{prims, nodes, order, /*pad=*/ldexp(S, -19)};

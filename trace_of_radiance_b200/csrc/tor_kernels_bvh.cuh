@@ -35,9 +35,8 @@ struct BvhRenderParams {
   uint32_t count_segments;
   unsigned long long* work_counter;
   unsigned long long* counters;  // [0] primary rays, [1] segments, [2] box-pair tests, [3] exact sphere tests
+  int32_t refill;                // waiting lanes of a warp that trigger a shade phase (kRefill in the text above)
 };
-
-static constexpr int kRefillDefault = 12;
 
 // One object of a leaf (or of the "always" list) against the ray: the reference's arithmetic
 // (spheres.nim:28-49 / moving_spheres.nim:39-67), operation for operation.  r2 = radius*radius and
@@ -69,7 +68,7 @@ __device__ __forceinline__ V3 rec_center(const double2* __restrict__ r, uint32_t
   return c0;
 }
 
-template <int BLOCK, int STAGE, int REFILL>
+template <int BLOCK, int STAGE>
 __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __grid_constant__ BvhRenderParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t stage_bar;
@@ -100,6 +99,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
   const double INF = __longlong_as_double(0x7ff0000000000000ll);
   const double t_min = 0.001;  // render.nim:28
   const unsigned long long total_px = (unsigned long long)P.nsel_rows * (unsigned long long)P.ncols;
+  const int refill = P.refill;
 
   Lane L;
   L.pix = v3(0, 0, 0);
@@ -188,7 +188,10 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
         ++L.sample;
         need_sample = true;
         if (L.sample >= P.spp) {
-          draw_pixel(P.pixels + 3ull * px, L.pix, P.inv_spp, P.inv_gamma);
+          double* out = P.pixels + 3ull * px;  // the sum; draw_kernel applies canvas.nim:47-54 afterwards
+          out[0] = L.pix.x;
+          out[1] = L.pix.y;
+          out[2] = L.pix.z;
           need_pixel = true;
           need_sample = false;
           active = false;
@@ -213,8 +216,8 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
           need_sample = true;
           break;
         }
-        double* out = P.pixels + 3ull * px;  // no samples: draw() of the zero colour (canvas.nim:49-54)
-        out[0] = out[1] = out[2] = detmath::pow(P.inv_spp * 0.0, P.inv_gamma);
+        double* out = P.pixels + 3ull * px;  // no samples: the zero colour goes through draw() (canvas.nim:49-54)
+        out[0] = out[1] = out[2] = 0.0;
       }
     }
     if (!__any_sync(0xffffffffu, active)) break;
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
       const int n_trav = __popc(__ballot_sync(0xffffffffu, trav));
       if (n_trav == 0) break;
       const int n_wait = __popc(__ballot_sync(0xffffffffu, active && trav_done));
-      if (n_wait >= REFILL) break;
+      if (n_wait >= refill) break;
       // ---- inner nodes until a leaf (cur < 0) or the end of the traversal
       if (trav) {
         while (cur >= 0) {
@@ -363,6 +366,15 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
       atomicAdd(P.counters + 3, test_count);
     }
   }
+}
+
+// canvas.nim:47-54 `draw` over the sums the render kernel left in the framebuffer: one thread per channel,
+// pixels[i] = pow(scale * pixels[i], gamma).  A separate pass so that the three pow() per pixel (double-double
+// log/exp, ~2000 instructions) run on full warps instead of lane by lane inside the render loop.
+__global__ void __launch_bounds__(256) draw_kernel(double* __restrict__ pixels, unsigned long long n, double inv_spp,
+                                                   double inv_gamma) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pixels[i] = detmath::pow(inv_spp * pixels[i], inv_gamma);
 }
 
 }  // namespace tor
