@@ -37,6 +37,15 @@ GAMMA = 2.2
 METRIC = "Mray/s (primary rays) at 1200x675 / 500 spp random_scene"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` on C2, from the committed ncu capture
+    (profiles/ncu_traffic.json, written from an `ncu --set full` run of tools/sweep.py); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel)
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -291,7 +300,10 @@ def _run_ours_on_stream(args, wl, rank, world_size, local_rank, dev, torch, dist
                     "DistributedRenderer.render (scene upload + kernel + all_gather + D2H)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak,
+                         "traffic": (ncu_traffic("render_bvh_kernel" if args.route == "bvh" else "render_exact_kernel")
+                                     if args.workload == "c2" and world_size == 1 else None),
+                         "peak_source": peak_src,
                          "kernel": "render_bvh_kernel" if args.route == "bvh" else "render_exact_kernel", "kernel_ms": statistics.mean(kernel_ms),
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "megakernel: HBM sees only the framebuffer write + one scene read; the binding roof is "
