@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python tools/gpu_quick.py 2>&1 | cut -c1-330
+for r in 16 20 24; do TOR_BVH_REFILL=$r python tools/sweep.py --dims 675 1200 500 2; done 2>&1 | tee gpurun_out/sweep_refill4.txt

@@ -32,19 +32,23 @@ namespace tor {
 
 // Two children per node, each with its own box.  child >= 0: inner node index; child < 0: leaf,
 // v = ~child, first record = v >> 4, count = v & 15 (0 = empty child).
-struct alignas(16) BvhNode {  // 64 bytes
+// The strides (80 and 144 bytes) are deliberately not powers of two: lanes of a warp read *different* nodes /
+// records with 16-byte shared-memory loads, and a stride of 20 (36) words spreads consecutive indices over all
+// eight 4-bank groups, where 64 (128) bytes would put every record on the same two (one) groups.
+struct alignas(16) BvhNode {  // 80 bytes, 56 used
   float lo0[3], hi0[3];
   float lo1[3], hi1[3];
   int32_t child0, child1;
-  int32_t pad[2];
+  int32_t pad[6];
 };
-static_assert(sizeof(BvhNode) == 64, "BvhNode layout");
+static_assert(sizeof(BvhNode) == 80, "BvhNode layout");
+static constexpr int kNodeStride16 = sizeof(BvhNode) / 16;
 
 // Everything the kernel needs about one object, in leaf order.  Derived fields are the SAME IEEE operations
 // the reference performs on the same inputs (so precomputing them changes no bit):
 //   dc = center1 - center0 (moving_spheres.nim:43), r2 = radius*radius (spheres.nim:32),
 //   inv_r = 1.0/radius (spheres.nim:43 through vec3s.nim:93-94).
-struct alignas(16) ObjRec {  // 128 bytes; the hit test of a static sphere reads only the first 48
+struct alignas(16) ObjRec {  // 144 bytes; the hit test of a static sphere reads only the first 48
   double c0[3];
   double r2;
   uint32_t kind_mat;  // kind | mat_kind << 8
@@ -55,8 +59,10 @@ struct alignas(16) ObjRec {  // 128 bytes; the hit test of a static sphere reads
   double t0, t1;  // time0, time1 (movers only)
   double albedo[3];
   double fuzz_or_ior;
+  double pad2[2];
 };
-static_assert(sizeof(ObjRec) == 128, "ObjRec layout");
+static_assert(sizeof(ObjRec) == 144, "ObjRec layout");
+static constexpr int kRecStride16 = sizeof(ObjRec) / 16;
 // kind_mat flag: a mover with time0 == +0.0 and time1 == 1.0, whose lerp parameter
 // (time - time0) / (time1 - time0) (moving_spheres.nim:41-42) is exactly `time` in IEEE arithmetic
 static constexpr uint32_t kObjUnitInterval = 1u << 16;

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
   qc.t0 = qc.t1 = qc.q = 0.0;
 
   auto test_rec = [&](int32_t ri) {
-    const double2* __restrict__ r = recs + 8 * ri;
+    const double2* __restrict__ r = recs + kRecStride16 * ri;
     const double2 a1 = r[1], a2 = r[2];
     const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
     const uint32_t orig = (uint32_t)((unsigned long long)__double_as_longlong(a2.x) >> 32);
@@ -139,20 +139,33 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
     double c = len2(oc) - a1.y;
     double disc = half_b * half_b - a * c;
     if (disc > 0) {
-      double root = sqrt(disc);
-      double t = INF;
-      double sol = (-half_b - root) / a;
-      if (t_min < sol) {
-        t = sol;
-      } else {
-        sol = (-half_b + root) / a;
-        if (t_min < sol) t = sol;
-      }
-      if (t < best_t || (t == best_t && orig < best_orig && t < INF)) {
-        best_t = t;
-        best_orig = orig;
-        best_rec = ri;
-        best_f = __double2float_ru(t);
+      const double root = sqrt(disc);
+      const double x1 = -half_b - root, x2 = -half_b + root;  // the reference's two numerators (spheres.nim:37-48)
+      // Two shortcuts that skip the IEEE divides without changing the outcome (division by a > 0 and rounding
+      // are monotonic; the 2^-40 margins cover the rounding of the products below):
+      //   x2 <= t_min*a*(1 - 2^-40)  =>  both roots round to <= t_min: no root in (t_min, inf)   [the sphere the
+      //                                   ray starts on, spheres behind the origin]
+      //   x1 >= best_t*a*(1 + 2^-40) =>  the first root is valid and strictly beyond the closest so far
+      const bool a_ok = a >= 1e-200 && a <= 1e200;
+      const double ta = t_min * a;
+      const double ba = best_t * a;
+      const bool none = a_ok && x2 <= ta * (1.0 - 0x1p-40);
+      const bool behind = a_ok && x1 >= ba * (1.0 + 0x1p-40);
+      if (!none && !behind) {
+        double t = INF;
+        double sol = x1 / a;
+        if (t_min < sol) {
+          t = sol;
+        } else {
+          sol = x2 / a;
+          if (t_min < sol) t = sol;
+        }
+        if (t < best_t || (t == best_t && orig < best_orig && t < INF)) {
+          best_t = t;
+          best_orig = orig;
+          best_rec = ri;
+          best_f = __double2float_ru(t);
+        }
       }
     }
   };
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
       if (P.max_depth <= 0) {  // render.nim:25 — the bounce loop body never runs
         sample_done = true;
       } else if (++seg_count, best_rec >= 0) {
-        const double2* __restrict__ r = recs + 8 * best_rec;
+        const double2* __restrict__ r = recs + kRecStride16 * best_rec;
         const double2 a2 = r[2], a6 = r[6], a7 = r[7];
         const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
         Surface S;
@@ -285,7 +298,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
       // ---- inner nodes until a leaf (cur < 0) or the end of the traversal
       if (trav) {
         while (cur >= 0) {
-          const float4* __restrict__ nd = nodes + 4 * cur;
+          const float4* __restrict__ nd = nodes + kNodeStride16 * cur;
           const float4 n0 = nd[0], n1 = nd[1], n2 = nd[2];
           const int4 n3 = *reinterpret_cast<const int4*>(nd + 3);
           ++box_count;
