@@ -18,12 +18,13 @@ def _book_cam(tor, aspect=16.0 / 9.0, t0=0.0, t1=1.0):
 
 
 def _check(tor, oracle, ctx, world, cam, h, w, spp, depth=50, gamma=2.2, rows=None):
-    """Both closest-hit routes (BVH = default, brute-force scan) against the oracle, bit for bit."""
+    """Brute-force scan, BVH with the row-major pixel queue, BVH with the longest-pixel-first queue (default; the
+    pre-pass only exists for spp >= 64): each against the oracle, bit for bit."""
     ocnt = {}
     ref = np.full((h, w, 3), -7.0)
     oracle.render(h, w, spp, cam.as_array(), world.objects, max_depth=depth, gamma=gamma, rows=rows, math="det",
                   counters=ocnt, out=ref)
-    for route in (tor.api.TOR_FLAG_BRUTE_FORCE, 0):
+    for route in (tor.api.TOR_FLAG_BRUTE_FORCE, tor.api.TOR_FLAG_ROW_MAJOR_QUEUE, 0):
         cv = tor.newCanvas(h, w, spp, gamma)
         cv.pixels[:] = -7.0  # rows that are not selected must stay untouched
         ctx.render(cv, cam, world, depth, flags=tor.api.TOR_FLAG_COUNT_SEGMENTS | route, rows=rows)

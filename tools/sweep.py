@@ -12,10 +12,15 @@ ctx = T.Context()
 world = T.random_scene().list()
 cam = T.camera((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 16.0 / 9.0, 0.1, 10.0, 0.0, 1.0)
 fl = T.api.TOR_FLAG_BRUTE_FORCE if "--brute" in sys.argv else 0
+if "--rowmajor" in sys.argv:
+    fl |= T.api.TOR_FLAG_ROW_MAJOR_QUEUE
 cv = T.newCanvas(h, w, spp, 2.2)
+rows = None
+if "--rowstep" in sys.argv:
+    rows = (0, h, int(sys.argv[sys.argv.index("--rowstep") + 1]))
 ms = []
 for _ in range(reps):
-    ctx.render(cv, cam, world, 50, flags=fl)
+    ctx.render(cv, cam, world, 50, flags=fl, rows=rows)
     ms.append(ctx.last_kernel_ms())
-print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("TOR_")}, "kernel_ms": ms,
+print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("TOR_")}, "kernel_ms": ms, "rows": rows,
                   "mray_s": h * w * spp / min(ms) / 1e3}), flush=True)

@@ -38,6 +38,7 @@ assert HITTABLE_DTYPE.itemsize == 112
 TOR_SPHERE, TOR_MOVING_SPHERE = 0, 1
 TOR_LAMBERTIAN, TOR_METAL, TOR_DIELECTRIC = 0, 1, 2
 TOR_FLAG_COUNT_SEGMENTS = 0x100
+TOR_FLAG_ROW_MAJOR_QUEUE = 0x400  # BVH route without the longest-pixel-first pre-pass (same image)
 TOR_FLAG_BRUTE_FORCE = 0x200  # scan every object like hittables_lists.nim:48-55 instead of the BVH (same image)
 
 EXPORTED_SYMBOLS = [

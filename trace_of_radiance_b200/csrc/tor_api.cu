@@ -32,7 +32,11 @@ struct DeviceState {
   size_t blob_cap = 0;
   double* d_pixels = nullptr;
   size_t pix_cap = 0;  // bytes
-  unsigned long long* d_work = nullptr;      // pixel queue head
+  unsigned long long* d_work = nullptr;      // pixel queue heads: [0] render, [1] cost pre-pass
+  uint32_t* d_cost = nullptr;                // per-pixel cost of the pre-pass, then the bucket offsets
+  uint32_t* d_order = nullptr;               // pixel queue order (most expensive first)
+  uint32_t* d_hist = nullptr;                // kCostBuckets counters
+  size_t order_cap = 0;                      // pixels
   unsigned long long* d_counters = nullptr;  // [0] primary rays, [1] segments, [2] box-pair tests, [3] exact tests
   bool scene_current = false;
   bool timed = false;
@@ -203,7 +207,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
   const bool count = (flags & TOR_FLAG_COUNT_SEGMENTS) != 0;
   const unsigned long long total_px = (unsigned long long)nsel * (unsigned long long)ncols;
   const unsigned long long want = (total_px + kBlock - 1) / kBlock;
-  TOR_CUDA(ctx, cudaMemsetAsync(d.d_work, 0, sizeof(unsigned long long), stream));
+  TOR_CUDA(ctx, cudaMemsetAsync(d.d_work, 0, 2 * sizeof(unsigned long long), stream));
 
   if (flags & TOR_FLAG_BRUTE_FORCE) {
     tor::RenderParams P;
@@ -255,6 +259,8 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     P.work_counter = d.d_work;
     P.counters = d.d_counters;
     P.refill = bvh_refill();
+    P.lanes_per_warp = 32;
+    if (P.refill > P.lanes_per_warp) P.refill = P.lanes_per_warp;
 
     BvhLaunchPlan plan = bvh_plan_for(P.bv, d.max_smem_per_sm);
     TOR_CUDA(ctx, cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
@@ -264,6 +270,50 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     unsigned long long cap = (unsigned long long)d.sm_count * (unsigned long long)per_sm;
     int grid = (int)(want < cap ? want : cap);
     if (timed) TOR_CUDA(ctx, cudaEventRecord(d.ev0, stream));
+
+    // Scheduling regime, from the number of pixels each lane will get (measured on B200):
+    //  * >= 4 pixels per lane: throughput-bound.  Longest-pixel-first queue order (tor_kernels_bvh.cuh): the
+    //    pre-pass renders the first `pre` samples of every pixel and keeps only their segment counts.
+    //  * < 2 pixels per lane: bound by the slowest pixel (a serial chain of spp * depth segments).  A lane advances
+    //    faster in a half-populated warp, so only 16 lanes per warp take pixels.
+    const unsigned long long lanes = (unsigned long long)grid * kBlock;
+    const int32_t pre = spp >= 64 ? (spp >= 256 ? 8 : 4) : 0;
+    const bool throughput_bound = total_px >= 4 * lanes;
+    if (total_px < 2 * lanes && total_px > lanes / 2) P.lanes_per_warp = 16;
+    if (const char* e = getenv("TOR_BVH_LANES")) {  // developer tuning knob
+      int v = atoi(e);
+      P.lanes_per_warp = v < 1 ? 1 : (v > 32 ? 32 : v);
+    }
+    if (P.refill > (P.lanes_per_warp * 5) / 8) P.refill = (P.lanes_per_warp * 5) / 8;
+    if (P.refill < 1) P.refill = 1;
+    if (pre > 0 && throughput_bound && !(flags & TOR_FLAG_ROW_MAJOR_QUEUE) && total_px < 0xffffffffull &&
+        max_depth > 0) {
+      if (total_px > d.order_cap) {
+        if (d.d_cost) cudaFree(d.d_cost);
+        if (d.d_order) cudaFree(d.d_order);
+        d.d_cost = d.d_order = nullptr;
+        d.order_cap = 0;
+        TOR_CUDA(ctx, cudaMalloc(&d.d_cost, total_px * sizeof(uint32_t)));
+        TOR_CUDA(ctx, cudaMalloc(&d.d_order, total_px * sizeof(uint32_t)));
+        d.order_cap = total_px;
+      }
+      tor::BvhRenderParams Q = P;
+      Q.spp = pre;
+      Q.count_segments = 0;
+      Q.work_counter = d.d_work + 1;
+      Q.cost = d.d_cost;
+      plan.fn<<<grid, kBlock, plan.smem, stream>>>(Q);
+      TOR_CUDA(ctx, cudaGetLastError());
+      TOR_CUDA(ctx, cudaMemsetAsync(d.d_hist, 0, tor::kCostBuckets * sizeof(uint32_t), stream));
+      const uint32_t n = (uint32_t)total_px;
+      const int sort_grid = (int)((n + 255) / 256 < (unsigned)(d.sm_count * 8) ? (n + 255) / 256 : d.sm_count * 8);
+      tor::cost_histogram_kernel<<<sort_grid, 256, 0, stream>>>(d.d_cost, n, d.d_hist);
+      tor::cost_offsets_kernel<<<1, tor::kCostBuckets, 0, stream>>>(d.d_hist);
+      tor::cost_scatter_kernel<<<sort_grid, 256, 0, stream>>>(d.d_cost, n, d.d_hist, d.d_order);
+      TOR_CUDA(ctx, cudaGetLastError());
+      ctx->launches += 4;
+      P.order = d.d_order;
+    }
     plan.fn<<<grid, kBlock, plan.smem, stream>>>(P);
     TOR_CUDA(ctx, cudaGetLastError());
     // canvas.nim:47-54 `draw` over the sums the render kernel left behind
@@ -327,7 +377,8 @@ int tor_ctx_create(const int* devices, int ndev, tor_ctx** out) {
     d.max_smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     bool ok = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&d.ev0) == cudaSuccess && cudaEventCreate(&d.ev1) == cudaSuccess &&
-              cudaMalloc(&d.d_work, sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&d.d_work, 2 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&d.d_hist, tor::kCostBuckets * sizeof(uint32_t)) == cudaSuccess &&
               cudaMalloc(&d.d_counters, 4 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMemset(d.d_counters, 0, 4 * sizeof(unsigned long long)) == cudaSuccess;
     ctx->devs.push_back(d);
@@ -349,6 +400,9 @@ void tor_ctx_destroy(tor_ctx* ctx) {
     if (d.d_blob) cudaFree(d.d_blob);
     if (d.d_pixels) cudaFree(d.d_pixels);
     if (d.d_work) cudaFree(d.d_work);
+    if (d.d_cost) cudaFree(d.d_cost);
+    if (d.d_order) cudaFree(d.d_order);
+    if (d.d_hist) cudaFree(d.d_hist);
     if (d.d_counters) cudaFree(d.d_counters);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);

@@ -36,6 +36,14 @@ struct BvhRenderParams {
   unsigned long long* work_counter;
   unsigned long long* counters;  // [0] primary rays, [1] segments, [2] box-pair tests, [3] exact sphere tests
   int32_t refill;                // waiting lanes of a warp that trigger a shade phase (kRefill in the text above)
+  // Pixel scheduling.  order == NULL: queue slot i is pixel i (row-major over the selected rows); otherwise pixel
+  // order[i].  cost != NULL marks the cost pre-pass: nothing is written to `pixels`, cost[pixel] receives the
+  // number of bounce segments the pixel's first `spp` samples took.
+  const uint32_t* order;
+  uint32_t* cost;
+  // Lanes of each warp that take pixels (1..32).  With few pixels per lane the render is bound by its slowest
+  // pixel, and a lane advances faster in a sparsely populated warp; the host picks the value (tor_api.cu).
+  int32_t lanes_per_warp;
 };
 
 // One object of a leaf (or of the "always" list) against the ray: the reference's arithmetic
@@ -108,8 +116,9 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
   L.d = v3(0, 0, 1);
   L.time = 0.0;
   L.row = L.col = L.sample = L.depth = 0;
-  unsigned long long px = 0;
-  bool active = false, need_pixel = true, need_sample = false;
+  uint32_t pid = 0;      // pixel index inside the selected rows
+  uint32_t pix_seg = 0;  // bounce segments of the current pixel
+  bool active = false, need_pixel = (tid & 31) < P.lanes_per_warp, need_sample = false;
   bool trav_done = false;  // the current segment's closest hit is final
   bool need_setup = false;  // a new segment needs its traversal state
   unsigned long long seg_count = 0, ray_count = 0, box_count = 0, test_count = 0;
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
       V3 color = v3(0, 0, 0);
       if (P.max_depth <= 0) {  // render.nim:25 — the bounce loop body never runs
         sample_done = true;
-      } else if (++seg_count, best_rec >= 0) {
+      } else if (++seg_count, ++pix_seg, best_rec >= 0) {
         const double2* __restrict__ r = recs + kRecStride16 * best_rec;
         const double2 a2 = r[2], a6 = r[6], a7 = r[7];
         const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
@@ -201,10 +210,14 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
         ++L.sample;
         need_sample = true;
         if (L.sample >= P.spp) {
-          double* out = P.pixels + 3ull * px;  // the sum; draw_kernel applies canvas.nim:47-54 afterwards
-          out[0] = L.pix.x;
-          out[1] = L.pix.y;
-          out[2] = L.pix.z;
+          if (P.cost) {
+            P.cost[pid] = pix_seg;
+          } else {
+            double* out = P.pixels + 3ull * pid;  // the sum; draw_kernel applies canvas.nim:47-54 afterwards
+            out[0] = L.pix.x;
+            out[1] = L.pix.y;
+            out[2] = L.pix.z;
+          }
           need_pixel = true;
           need_sample = false;
           active = false;
@@ -216,11 +229,13 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
       need_pixel = false;
       active = false;
       for (;;) {
-        px = atomicAdd(P.work_counter, 1ull);
-        if (px >= total_px) break;
+        const unsigned long long slot = atomicAdd(P.work_counter, 1ull);
+        if (slot >= total_px) break;
+        pid = P.order ? P.order[slot] : (uint32_t)slot;
+        pix_seg = 0;
         if (P.spp > 0) {
-          int32_t ri = (int32_t)(px / (unsigned long long)P.ncols);
-          L.col = (int32_t)(px - (unsigned long long)ri * (unsigned long long)P.ncols);
+          int32_t ri = (int32_t)(pid / (uint32_t)P.ncols);
+          L.col = (int32_t)(pid - (uint32_t)ri * (uint32_t)P.ncols);
           L.row = P.row_begin + ri * P.row_step;
           rng_seed_pixel(L.rng, L.row, L.col);  // render.nim:59-60
           L.pix = v3(0, 0, 0);
@@ -229,7 +244,7 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
           need_sample = true;
           break;
         }
-        double* out = P.pixels + 3ull * px;  // no samples: the zero colour goes through draw() (canvas.nim:49-54)
+        double* out = P.pixels + 3ull * pid;  // no samples: the zero colour goes through draw() (canvas.nim:49-54)
         out[0] = out[1] = out[2] = 0.0;
       }
     }
@@ -378,6 +393,52 @@ __global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __
       atomicAdd(P.counters + 2, box_count);
       atomicAdd(P.counters + 3, test_count);
     }
+  }
+}
+
+// ------------------------------------------------------------------- longest-pixel-first scheduling
+// A pixel's samples are sequential (one RNG stream, render.nim:59-67), so the render cannot end before its most
+// expensive pixel does (glass: up to 50 bounces per sample; measured ~95 ms at C2).  A cost pre-pass (the render
+// kernel itself on the first few samples, counting segments) and this counting sort put expensive pixels at the
+// head of the queue, so they start first and cheap pixels fill the tail.  The order cannot change the image.
+static constexpr int kCostBuckets = 1024;
+
+__global__ void __launch_bounds__(256) cost_histogram_kernel(const uint32_t* __restrict__ cost, uint32_t n,
+                                                             uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[kCostBuckets];
+  for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t c = cost[i];
+    atomicAdd(&h[c < kCostBuckets ? c : kCostBuckets - 1], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x)
+    if (h[i]) atomicAdd(&hist[i], h[i]);
+}
+
+// hist[b] := number of pixels in buckets above b (queue offset of bucket b, most expensive bucket first)
+__global__ void __launch_bounds__(kCostBuckets) cost_offsets_kernel(uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s[kCostBuckets];
+  const int t = threadIdx.x;            // t = 0 is the most expensive bucket
+  const int b = kCostBuckets - 1 - t;
+  s[t] = hist[b];
+  __syncthreads();
+  for (int ofs = 1; ofs < kCostBuckets; ofs <<= 1) {  // inclusive scan
+    uint32_t v = t >= ofs ? s[t - ofs] : 0u;
+    __syncthreads();
+    s[t] += v;
+    __syncthreads();
+  }
+  hist[b] = s[t] - hist[b];  // exclusive
+}
+
+__global__ void __launch_bounds__(256) cost_scatter_kernel(const uint32_t* __restrict__ cost, uint32_t n,
+                                                           uint32_t* __restrict__ offsets, uint32_t* __restrict__ order) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t c = cost[i];
+    uint32_t pos = atomicAdd(&offsets[c < kCostBuckets ? c : kCostBuckets - 1], 1u);
+    order[pos] = i;
   }
 }
 
