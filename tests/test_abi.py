@@ -92,3 +92,19 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cc", ".hpp", ".h")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_lib" not in text and "tor_oracle" not in text and "liboracle" not in text, f
+
+
+def test_animation_helper_equals_oracle(tor, oracle):  # scenes_animated.nim:90-225
+    mine = tor.Animation(height=36, width=64, t_max=0.2).scenes(skip=6)
+    ref = oracle.Animation(height=36, width=64, t_max=0.2)
+    frames = 0
+    for cam, world in mine:
+        cam_ref, objs_ref = ref.next_frame(skip=6)
+        assert cam.as_array().tobytes() == np.ascontiguousarray(cam_ref).tobytes()
+        assert world.objects.tobytes() == np.ascontiguousarray(objs_ref).tobytes()
+        assert len(world) == 1601
+        frames += 1
+    assert frames == 7  # t = 0, 0.03, ..., 0.18 in float32 steps of 6 * 0.005
+    # the frame count of the full C4 animation (t_max = 9.0) comes from float32 accumulation: 300
+    n = sum(1 for _ in tor.Animation(height=8, width=8, t_max=9.0).scenes(skip=6))
+    assert n == 300

@@ -7,6 +7,7 @@ no CPU fallback: importing works anywhere, but every compute call fails loudly w
 sm_100a library and a CUDA device.
 """
 from .api import (  # noqa: F401
+    Animation,
     HITTABLE_DTYPE,
     Camera,
     Canvas,

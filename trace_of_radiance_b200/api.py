@@ -44,7 +44,8 @@ TOR_FLAG_BRUTE_FORCE = 0x200  # scan every object like hittables_lists.nim:48-55
 EXPORTED_SYMBOLS = [
     "tor_abi_version", "tor_ctx_create", "tor_ctx_destroy", "tor_last_error", "tor_render", "tor_render_rows",
     "tor_scene_upload", "tor_render_device_async", "tor_sync", "tor_get_counters", "tor_last_kernel_ms",
-    "tor_launch_count", "tor_measure_fp64_peak", "tor_get_traversal_counters", "tor_scene_info", "tor_camera_make", "tor_random_scene", "tor_export_ppm", "tor_quantise_rgb8",
+    "tor_launch_count", "tor_measure_fp64_peak", "tor_get_traversal_counters", "tor_scene_info", "tor_camera_make", "tor_random_scene", "tor_export_ppm", "tor_quantise_rgb8", "tor_animation_create",
+    "tor_animation_next_frame", "tor_animation_destroy",
 ]
 
 
@@ -107,6 +108,12 @@ def load_library():
     L.tor_camera_make.restype = None
     L.tor_random_scene.argtypes = [C.c_uint64, C.c_int32, vp, C.c_int64]
     L.tor_random_scene.restype = C.c_int64
+    L.tor_animation_create.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float]
+    L.tor_animation_create.restype = vp
+    L.tor_animation_next_frame.argtypes = [vp, C.c_int32, C.POINTER(_CCamera), vp, C.c_int64]
+    L.tor_animation_next_frame.restype = C.c_int64
+    L.tor_animation_destroy.argtypes = [vp]
+    L.tor_animation_destroy.restype = None
     L.tor_export_ppm.argtypes = [C.POINTER(_CCanvas), C.c_char_p]
     L.tor_quantise_rgb8.argtypes = [C.POINTER(_CCanvas), C.POINTER(C.c_uint8)]
     _lib = L
@@ -188,6 +195,35 @@ def random_scene(seed=0xFACADE, half=11):
     buf = np.zeros(n, dtype=HITTABLE_DTYPE)
     L.tor_random_scene(seed, half, buf.ctypes.data, n)
     return Scene(buf)
+
+
+class Animation:
+    """scenes_animated.nim:57-225: `random_moving_spheres` + `iterator scenes(anim, skip)`.
+
+        for cam, world in tor.Animation(height=144, width=256).scenes(skip=6): tor.render(canvas, cam, world, 50)
+    """
+
+    def __init__(self, seed=0xFACADE, height=144, width=256, dt=0.005, t_min=0.0, t_max=9.0):
+        self.L = load_library()
+        self.h = self.L.tor_animation_create(seed, height, width, dt, t_min, t_max)
+
+    def scenes(self, skip=6):
+        cap = 40 * 40 + 4
+        while True:
+            cam = _CCamera()
+            buf = np.zeros(cap, dtype=HITTABLE_DTYPE)
+            n = self.L.tor_animation_next_frame(self.h, skip, C.byref(cam), buf.ctypes.data, cap)
+            if n <= 0:
+                return
+            yield Camera(cam), HittableList(buf[:n])
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.tor_animation_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
 
 
 # ---------------------------------------------------------------------------------- camera

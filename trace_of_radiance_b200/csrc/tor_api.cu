@@ -89,6 +89,7 @@ struct BvhLaunchPlan {
   BvhKernelFn fn;
   int stage;
   size_t smem;
+  int block;
 };
 
 LaunchPlan plan_for(const tor::SceneView& sv, int max_smem_optin) {
@@ -103,11 +104,27 @@ LaunchPlan plan_for(const tor::SceneView& sv, int max_smem_optin) {
 
 // The hierarchy is staged in shared memory only while two CTAs still fit on an SM (the traversal is
 // latency-bound and wants the warps); beyond that the nodes, then nothing, and L1/L2 serve the rest.
-BvhLaunchPlan bvh_plan_for(const tor::BvhView& bv, int max_smem_per_sm) {
-  const size_t budget = (size_t)max_smem_per_sm / 2 - 2048;
-  if (bv.total_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<kBlock, 2>, 2, bv.total_bytes};
-  if (bv.nodes_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<kBlock, 1>, 1, bv.nodes_bytes};
-  return BvhLaunchPlan{tor::render_bvh_kernel<kBlock, 0>, 0, 0};
+template <int B>
+BvhLaunchPlan bvh_plan_b(const tor::BvhView& bv, size_t budget) {
+  if (bv.total_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<B, 2>, 2, bv.total_bytes, B};
+  if (bv.nodes_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<B, 1>, 1, bv.nodes_bytes, B};
+  return BvhLaunchPlan{tor::render_bvh_kernel<B, 0>, 0, 0, B};
+}
+
+BvhLaunchPlan bvh_plan_for(const tor::BvhView& bv, int max_smem_per_sm, int max_smem_optin) {
+  static const int block = [] {  // developer tuning knob: CTA size (registers per lane follow from it)
+    const char* e = getenv("TOR_BVH_BLOCK");
+    return e ? atoi(e) : kBlock;
+  }();
+  const size_t half = (size_t)max_smem_per_sm / 2 - 2048;
+  const size_t whole = (size_t)max_smem_optin;
+  switch (block) {
+    case 384: return bvh_plan_b<384>(bv, half);
+    case 512: return bvh_plan_b<512>(bv, whole);
+    case 768: return bvh_plan_b<768>(bv, whole);
+    case 1024: return bvh_plan_b<1024>(bv, whole);
+    default: return bvh_plan_b<kBlock>(bv, half);
+  }
 }
 
 // kRefill of the BVH kernel (tor_kernels_bvh.cuh).  The environment variable is a developer tuning knob;
@@ -262,13 +279,15 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     P.lanes_per_warp = 32;
     if (P.refill > P.lanes_per_warp) P.refill = P.lanes_per_warp;
 
-    BvhLaunchPlan plan = bvh_plan_for(P.bv, d.max_smem_per_sm);
+    BvhLaunchPlan plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin);
+    const int block = plan.block;
     TOR_CUDA(ctx, cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     int per_sm = 0;
-    TOR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, kBlock, plan.smem));
+    TOR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, block, plan.smem));
     if (per_sm < 1) return fail(ctx, TOR_ERR_CUDA, "render kernel does not fit on an SM");
     unsigned long long cap = (unsigned long long)d.sm_count * (unsigned long long)per_sm;
-    int grid = (int)(want < cap ? want : cap);
+    const unsigned long long want_b = (total_px + block - 1) / block;
+    int grid = (int)(want_b < cap ? want_b : cap);
     if (timed) TOR_CUDA(ctx, cudaEventRecord(d.ev0, stream));
 
     // Scheduling regime, from the number of pixels each lane will get (measured on B200):
@@ -276,7 +295,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     //    pre-pass renders the first `pre` samples of every pixel and keeps only their segment counts.
     //  * < 2 pixels per lane: bound by the slowest pixel (a serial chain of spp * depth segments).  A lane advances
     //    faster in a half-populated warp, so only 16 lanes per warp take pixels.
-    const unsigned long long lanes = (unsigned long long)grid * kBlock;
+    const unsigned long long lanes = (unsigned long long)grid * block;
     const int32_t pre = spp >= 64 ? (spp >= 256 ? 8 : 4) : 0;
     const bool throughput_bound = total_px >= 4 * lanes;
     if (total_px < 2 * lanes && total_px > lanes / 2) P.lanes_per_warp = 16;
@@ -302,7 +321,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       Q.count_segments = 0;
       Q.work_counter = d.d_work + 1;
       Q.cost = d.d_cost;
-      plan.fn<<<grid, kBlock, plan.smem, stream>>>(Q);
+      plan.fn<<<grid, block, plan.smem, stream>>>(Q);
       TOR_CUDA(ctx, cudaGetLastError());
       TOR_CUDA(ctx, cudaMemsetAsync(d.d_hist, 0, tor::kCostBuckets * sizeof(uint32_t), stream));
       const uint32_t n = (uint32_t)total_px;
@@ -314,7 +333,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       ctx->launches += 4;
       P.order = d.d_order;
     }
-    plan.fn<<<grid, kBlock, plan.smem, stream>>>(P);
+    plan.fn<<<grid, block, plan.smem, stream>>>(P);
     TOR_CUDA(ctx, cudaGetLastError());
     // canvas.nim:47-54 `draw` over the sums the render kernel left behind
     const unsigned long long nch = total_px * 3ull;

@@ -76,6 +76,34 @@ tor_hittable mk_sphere(V c, double r, uint32_t mat, V albedo, double fz) {
   return h;
 }
 
+// ---- scenes_animated.nim:42-69 ----
+struct AnimSphere {
+  double velocity, pos_y, coef_restitution, x, z, radius;
+  uint32_t mat_kind;
+  V albedo;
+  double fuzz_or_ior;
+};
+struct Animation {
+  int32_t nrows, ncols;
+  float dt, t_min, t_max, t;  // ATime is float32 (scenes_animated.nim:36): the frame count depends on it
+  double look_from_angle;
+  bool started;
+  std::vector<AnimSphere> spheres;
+};
+
+void anim_step(Animation& an) {  // scenes_animated.nim:156-174: camera first, then physics
+  an.look_from_angle -= 2.0 * 3.141592653589793 / 1200.0;
+  an.t += an.dt;
+  const double G = 9.80665, small_radius = 0.2;
+  for (AnimSphere& s : an.spheres) {
+    if (s.velocity < 0.0 && s.pos_y < small_radius)
+      s.velocity = -s.coef_restitution * s.velocity;
+    else
+      s.velocity -= G * (double)an.dt;
+    s.pos_y += s.velocity * (double)an.dt;
+  }
+}
+
 int ppm_level(double c) {  // io/ppm.nim:15-16 + safe_math.nim:10-14; NaN (UB in the reference) -> 0
   if (c != c) return 0;
   double cl = c < 0.0 ? 0.0 : (c > 0.999 ? 0.999 : c);
@@ -150,6 +178,95 @@ int64_t tor_random_scene(uint64_t seed, int32_t half, tor_hittable* out, int64_t
   w.push_back(mk_sphere(V{-4, 1, 0}, 1.0, TOR_LAMBERTIAN, V{0.4, 0.2, 0.1}, 0));
   w.push_back(mk_sphere(V{4, 1, 0}, 1.0, TOR_METAL, V{0.7, 0.6, 0.5}, 0.0));
   int64_t n = (int64_t)w.size();
+  if (out)
+    for (int64_t i = 0; i < n && i < cap; ++i) out[i] = w[(size_t)i];
+  return n;
+}
+
+// scenes_animated.nim:90-154 `random_moving_spheres` with rng.seed(seed) (trace_of_radiance_animation.nim:61-63)
+void* tor_animation_create(uint64_t seed, int32_t height, int32_t width, float dt, float t_min, float t_max) {
+  HostRng rng(seed);
+  Animation* an = new Animation();
+  an->nrows = height;
+  an->ncols = width;
+  an->dt = dt;
+  an->t_min = t_min;
+  an->t_max = t_max;
+  an->t = 0.0f;
+  an->look_from_angle = 2 * 3.141592653589793;
+  an->started = false;
+  const double small_radius = 0.2;
+  for (int a = -20; a < 20; ++a)
+    for (int b = -20; b < 20; ++b) {
+      double cx = (double)a + 0.9 * rng.u01();
+      double cz = (double)b + 0.9 * rng.u01();
+      V center{cx, small_radius, cz};
+      if (len(sub(center, V{4, small_radius, 0})) > 0.9) {
+        double choose = rng.u01();
+        AnimSphere s;
+        s.x = center.x;
+        s.pos_y = center.y;
+        s.z = center.z;
+        s.radius = small_radius;
+        if (choose < 0.65) {
+          V a1{0, 0, 0}, a2{0, 0, 0};
+          a1.x = rng.u01(); a1.y = rng.u01(); a1.z = rng.u01();
+          a2.x = rng.u01(); a2.y = rng.u01(); a2.z = rng.u01();
+          s.albedo = V{a1.x * a2.x, a1.y * a2.y, a1.z * a2.z};
+          s.coef_restitution = 0.6;
+          s.velocity = 10.0 + (4 * rng.u01() - 2.0);  // rng.random(float32) is the single float64 draw
+          s.mat_kind = TOR_LAMBERTIAN;
+          s.fuzz_or_ior = 0;
+        } else if (choose < 0.95) {
+          V al{0, 0, 0};
+          al.x = rng.urange(0.5, 1); al.y = rng.urange(0.5, 1); al.z = rng.urange(0.5, 1);
+          s.albedo = al;
+          double fuzz = rng.umax(0.5);
+          s.coef_restitution = 0.5;
+          s.velocity = 10.0 + (4 * rng.u01() - 2.0);
+          s.mat_kind = TOR_METAL;
+          s.fuzz_or_ior = fuzz <= 1.0 ? fuzz : 1.0;
+        } else {
+          s.albedo = V{0, 0, 0};
+          s.coef_restitution = 0.5;
+          s.velocity = 10.0 + (4 * rng.u01() - 2.0);
+          s.mat_kind = TOR_DIELECTRIC;
+          s.fuzz_or_ior = 1.5;
+        }
+        an->spheres.push_back(s);
+      }
+    }
+  return an;
+}
+
+void tor_animation_destroy(void* h) { delete (Animation*)h; }
+
+// One iteration of `iterator scenes(anim, skip)` (scenes_animated.nim:176-225): the frame is produced, then the
+// physics advances `skip` steps.  Returns the object count of the frame (written to out[0 .. min(count, cap))),
+// or 0 when t >= t_max (the iterator is exhausted).
+int64_t tor_animation_next_frame(void* h, int32_t skip, tor_camera* cam, tor_hittable* out, int64_t cap) {
+  if (!h || !cam) return TOR_ERR_INVALID_ARG;
+  Animation& an = *(Animation*)h;
+  if (!an.started) {
+    while (an.t < an.t_min) anim_step(an);
+    an.started = true;
+  } else {
+    for (int i = 0; i < skip; ++i) anim_step(an);
+  }
+  if (!(an.t < an.t_max)) return 0;
+  const double aspect_ratio = (double)an.ncols / (double)an.nrows;
+  const double r = sqrt(200.0);
+  const double from[3] = {r * cos(an.look_from_angle), 2.0, r * sin(an.look_from_angle)};
+  const double at[3] = {4, 1, 0}, up[3] = {0, 1, 0};
+  tor_camera_make(cam, from, at, up, 20.0, aspect_ratio, 0.1, 10.0, 0.0, 0.0);
+  std::vector<tor_hittable> w;
+  w.push_back(mk_sphere(V{0, -1000, 0}, 1000, TOR_LAMBERTIAN, V{0.5, 0.5, 0.5}, 0));
+  for (const AnimSphere& s : an.spheres)
+    w.push_back(mk_sphere(V{s.x, s.pos_y, s.z}, s.radius, s.mat_kind, s.albedo, s.fuzz_or_ior));
+  w.push_back(mk_sphere(V{0, 1, 0}, 1.0, TOR_DIELECTRIC, V{0, 0, 0}, 1.5));
+  w.push_back(mk_sphere(V{-4, 1, 0}, 1.0, TOR_LAMBERTIAN, V{0.4, 0.2, 0.1}, 0));
+  w.push_back(mk_sphere(V{4, 1, 0}, 1.0, TOR_METAL, V{0.7, 0.6, 0.5}, 0.0));
+  const int64_t n = (int64_t)w.size();
   if (out)
     for (int64_t i = 0; i < n && i < cap; ++i) out[i] = w[(size_t)i];
   return n;

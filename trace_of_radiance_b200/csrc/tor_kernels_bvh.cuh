@@ -77,7 +77,7 @@ __device__ __forceinline__ V3 rec_center(const double2* __restrict__ r, uint32_t
 }
 
 template <int BLOCK, int STAGE>
-__global__ void __launch_bounds__(BLOCK, 512 / BLOCK) render_bvh_kernel(const __grid_constant__ BvhRenderParams P) {
+__global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 384 ? 2 : 1)) render_bvh_kernel(const __grid_constant__ BvhRenderParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t stage_bar;
 
