@@ -119,6 +119,8 @@ BvhLaunchPlan bvh_plan_for(const tor::BvhView& bv, int max_smem_per_sm, int max_
   const size_t half = (size_t)max_smem_per_sm / 2 - 2048;
   const size_t whole = (size_t)max_smem_optin;
   switch (block) {
+    case 288: return bvh_plan_b<288>(bv, half);
+    case 320: return bvh_plan_b<320>(bv, half);
     case 384: return bvh_plan_b<384>(bv, half);
     case 512: return bvh_plan_b<512>(bv, whole);
     case 768: return bvh_plan_b<768>(bv, whole);
