@@ -19,6 +19,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -86,7 +87,16 @@ struct PackedBvh {
   int n_leaves = 0;
 };
 
-static constexpr int kBvhMaxLeaf = 4;
+// objects per leaf: at most 15 fit the leaf reference; developer knob TOR_BVH_LEAF
+static inline int bvh_max_leaf() {
+  static const int v = [] {
+    const char* e = getenv("TOR_BVH_LEAF");
+    int n = e ? atoi(e) : 4;
+    return n < 1 ? 1 : (n > 15 ? 15 : n);
+  }();
+  return v;
+}
+#define kBvhMaxLeaf (::tor::bvh_max_leaf())
 static constexpr int kBvhStackDepth = 40;  // >= max tree depth (forced median splits below bound it)
 
 namespace bvh_detail {
@@ -190,7 +200,12 @@ struct Builder {
 
     // binned surface-area heuristic on every axis
     constexpr int kBins = 16;
-    const double c_trav = 1.0, c_isect = 0.7;
+    // developer knob TOR_BVH_ISECT: cost of one sphere test relative to one node visit
+    static const double c_isect_env = [] {
+      const char* e = getenv("TOR_BVH_ISECT");
+      return e ? atof(e) : 0.7;
+    }();
+    const double c_trav = 1.0, c_isect = c_isect_env;
     double best_cost = INFINITY;
     int best_axis = -1, best_bin = -1;
     for (int ax = 0; ax < 3; ++ax) {
