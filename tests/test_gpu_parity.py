@@ -277,3 +277,30 @@ def test_device_resident_entry_point(tor, gpu_ctx):
     stream.synchronize()
     assert dev.cpu().numpy().tobytes() == host.pixels[2:30:3].tobytes()
     assert gpu_ctx.launch_count() > 0 and gpu_ctx.last_kernel_ms() > 0
+
+
+def test_rgb8_output_equals_ppm_quantisation(tor, oracle, gpu_ctx):
+    """tor_render_rgb8: io/ppm.nim:14-27 quantisation on the device, PPM row order."""
+    world, cam = tor.random_scene().list(), _book_cam(tor)
+    cv = tor.newCanvas(45, 80, 8, 2.2)
+    gpu_ctx.render(cv, cam, world, 50)
+    rgb = gpu_ctx.render_rgb8(cv, cam, world, 50)
+    assert rgb.dtype == np.uint8 and rgb.shape == (45, 80, 3)
+    assert np.array_equal(rgb, cv.toRGB8())
+    ref = oracle.render(45, 80, 8, cam.as_array(), world.objects, math="det")
+    assert np.array_equal(rgb, oracle.quantise_rgb8(ref))
+    nan = tor.newCanvas(5, 7, 0, 2.2)  # spp == 0: a NaN image (canvas.nim:49-54) quantises to 0
+    assert not gpu_ctx.render_rgb8(nan, cam, world, 50).any()
+
+
+def test_animation_frame_pipeline(tor, oracle):
+    """render_animation: several frames in flight on separate contexts; every frame equals the oracle's."""
+    frames = {}
+    n = tor.render_animation(tor.Animation(height=27, width=48, t_max=9.0), samples_per_pixel=4, in_flight=3,
+                             on_frame=lambda i, rgb: frames.__setitem__(i, rgb.copy()), max_frames=7)
+    assert n == 7 and sorted(frames) == list(range(7))
+    an = oracle.Animation(height=27, width=48, t_max=9.0)
+    for i in range(7):
+        cam_arr, objs = an.next_frame(skip=6)
+        ref = oracle.render(27, 48, 4, cam_arr, objs, math="det")
+        assert np.array_equal(frames[i], oracle.quantise_rgb8(ref)), i

@@ -53,6 +53,17 @@ out["c4"] = {"frames_timed": frames, "objects_per_frame": len(w), "kernel_ms_per
              "extrapolated_300_frames_s": wall / frames * 300, "scene_info": ctx.scene_info()}
 print("c4", out["c4"], flush=True)
 
+# ---- C4 through the frame pipeline (4 frames in flight, RGB8 output, pinned host buffers)
+for inflight in (1, 2, 4, 8):
+    t0 = time.perf_counter()
+    n = T.render_animation(T.Animation(height=144, width=256, t_max=9.0), samples_per_pixel=100, in_flight=inflight,
+                           max_frames=48)
+    wall = time.perf_counter() - t0
+    out[f"c4_pipeline_{inflight}_in_flight"] = {"frames": n, "wall_ms_per_frame": wall / n * 1e3,
+                                                "mray_s": 144 * 256 * 100 * n / wall / 1e6,
+                                                "extrapolated_300_frames_s": wall / n * 300}
+    print("c4 pipeline", inflight, out[f"c4_pipeline_{inflight}_in_flight"], flush=True)
+
 # ---- C5: 10 004 spheres, 3840x2160, 2000 spp, every 20th row
 big = T.random_scene(0xFACADE, 50).list()
 cv = T.newCanvas(2160, 3840, 2000, 2.2)
@@ -66,7 +77,7 @@ print("c5", out["c5_sample"], flush=True)
 
 # ---- object-count sweep at 1200x675 / 50 spp
 sweep = []
-for half in (0, 1, 2, 4, 8, 11, 16, 23, 32, 50):
+for half in (11,) if "--quick" in sys.argv else (0, 1, 2, 4, 8, 11, 16, 23, 32, 50):
     w = T.random_scene(0xFACADE, half).list()
     cv = T.newCanvas(675, 1200, 50, 2.2)
     row = {"half": half, "objects": len(w)}

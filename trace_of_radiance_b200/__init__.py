@@ -8,6 +8,8 @@ sm_100a library and a CUDA device.
 """
 from .api import (  # noqa: F401
     Animation,
+    PinnedBuffer,
+    render_animation,
     HITTABLE_DTYPE,
     Camera,
     Canvas,

@@ -39,13 +39,15 @@ TOR_SPHERE, TOR_MOVING_SPHERE = 0, 1
 TOR_LAMBERTIAN, TOR_METAL, TOR_DIELECTRIC = 0, 1, 2
 TOR_FLAG_COUNT_SEGMENTS = 0x100
 TOR_FLAG_ROW_MAJOR_QUEUE = 0x400  # BVH route without the longest-pixel-first pre-pass (same image)
+TOR_FLAG_FULL_WARPS = 0x800  # all 32 lanes of a warp take pixels even for small renders (throughput over latency)
 TOR_FLAG_BRUTE_FORCE = 0x200  # scan every object like hittables_lists.nim:48-55 instead of the BVH (same image)
 
 EXPORTED_SYMBOLS = [
     "tor_abi_version", "tor_ctx_create", "tor_ctx_destroy", "tor_last_error", "tor_render", "tor_render_rows",
     "tor_scene_upload", "tor_render_device_async", "tor_sync", "tor_get_counters", "tor_last_kernel_ms",
     "tor_launch_count", "tor_measure_fp64_peak", "tor_get_traversal_counters", "tor_scene_info", "tor_camera_make", "tor_random_scene", "tor_export_ppm", "tor_quantise_rgb8", "tor_animation_create",
-    "tor_animation_next_frame", "tor_animation_destroy",
+    "tor_animation_next_frame", "tor_animation_destroy", "tor_render_rgb8", "tor_render_rgb8_async", "tor_host_alloc",
+    "tor_host_free",
 ]
 
 
@@ -93,6 +95,13 @@ def load_library():
     L.tor_last_error.restype = C.c_char_p
     L.tor_render.argtypes = [vp, C.POINTER(_CCanvas), C.POINTER(_CCamera), vp, C.c_int64, C.c_int64, C.c_int64, C.c_uint32]
     L.tor_render_rows.argtypes = L.tor_render.argtypes + [C.c_int32, C.c_int32, C.c_int32]
+    L.tor_render_rgb8.argtypes = [vp, C.POINTER(_CCanvas), C.POINTER(_CCamera), vp, C.c_int64, C.c_int64, C.c_int64,
+                                  C.c_uint32, vp]
+    L.tor_render_rgb8_async.argtypes = L.tor_render_rgb8.argtypes
+    L.tor_host_alloc.argtypes = [C.c_size_t]
+    L.tor_host_alloc.restype = vp
+    L.tor_host_free.argtypes = [vp]
+    L.tor_host_free.restype = None
     L.tor_scene_upload.argtypes = [vp, C.POINTER(_CCamera), vp, C.c_int64, C.c_int64]
     L.tor_render_device_async.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int64, C.c_uint32,
                                           C.c_int32, C.c_int32, C.c_int32, vp]
@@ -205,6 +214,7 @@ class Animation:
 
     def __init__(self, seed=0xFACADE, height=144, width=256, dt=0.005, t_min=0.0, t_max=9.0):
         self.L = load_library()
+        self.height, self.width = int(height), int(width)
         self.h = self.L.tor_animation_create(seed, height, width, dt, t_min, t_max)
 
     def scenes(self, skip=6):
@@ -335,6 +345,18 @@ class Context:
             self._check(self.L.tor_render_rows(self.h, C.byref(c), C.byref(cam.c), objs.ctypes.data, len(objs),
                                                objs.dtype.itemsize, max_depth, flags, rb, re, rs))
 
+    def render_rgb8(self, canvas, cam, world, max_depth, flags=0, out=None, wait=True):
+        """render + io/ppm.nim quantisation on the device: returns the (nrows, ncols, 3) uint8 image in PPM row
+        order.  wait=False enqueues only (pass a pinned `out`, see PinnedBuffer, and call sync())."""
+        if out is None:
+            out = np.empty((canvas.nrows, canvas.ncols, 3), dtype=np.uint8)
+        c = _CCanvas(None, canvas.nrows, canvas.ncols, canvas.samples_per_pixel, canvas.gamma_correction)
+        objs = world.objects
+        fn = self.L.tor_render_rgb8 if wait else self.L.tor_render_rgb8_async
+        self._check(fn(self.h, C.byref(c), C.byref(cam.c), objs.ctypes.data, len(objs), objs.dtype.itemsize, max_depth,
+                       flags, out.ctypes.data))
+        return out
+
     def render_raw(self, canvas, cam, objects_ptr, length, stride, max_depth, flags=0):
         """Same call with an explicit (pointer, len, stride) — e.g. the 120-byte Nim variant encoding."""
         c = canvas._c()
@@ -384,6 +406,66 @@ class Context:
 
     def launch_count(self):
         return int(self.L.tor_launch_count(self.h))
+
+
+class PinnedBuffer:
+    """Page-locked host memory (tor_host_alloc) viewed as a numpy array."""
+
+    def __init__(self, shape, dtype=np.uint8):
+        self.L = load_library()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = self.L.tor_host_alloc(n)
+        if not self.ptr:
+            raise MemoryError("tor_host_alloc failed")
+        self.array = np.ctypeslib.as_array((C.c_uint8 * n).from_address(self.ptr)).view(dtype).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.L.tor_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def render_animation(animation, samples_per_pixel=100, max_depth=50, gamma_correction=2.2, skip=6, in_flight=4,
+                     devices=None, on_frame=None, max_frames=None, flags=None):
+    """The frame loop of trace_of_radiance_animation.nim:173-199 (for camera, scene in scenes(animation, skip):
+    canvas.render(camera, scene.list(), max_depth); export) with `in_flight` frames enqueued at once, each on its own
+    context (= its own stream), so that small frames (256x144) keep the GPU full.  on_frame(index, rgb8) is called in
+    frame order with the PPM-order uint8 image; returns the number of frames."""
+    h, w = animation_dims(animation)
+    canvas = Canvas.__new__(Canvas)
+    canvas.nrows, canvas.ncols, canvas.samples_per_pixel = h, w, int(samples_per_pixel)
+    canvas.gamma_correction = float(np.float32(gamma_correction))
+    canvas.pixels = None
+    ctxs = [Context(devices) for _ in range(in_flight)]
+    bufs = [PinnedBuffer((h, w, 3)) for _ in range(in_flight)]
+    pending = [None] * in_flight
+    n = 0
+    for i, (cam, world) in enumerate(animation.scenes(skip=skip)):
+        if max_frames is not None and i >= max_frames:
+            break
+        k = i % in_flight
+        if pending[k] is not None:
+            ctxs[k].sync()
+            if on_frame:
+                on_frame(pending[k], bufs[k].array)
+        ctxs[k].render_rgb8(canvas, cam, world, max_depth, out=bufs[k].array, wait=False,
+                            flags=(TOR_FLAG_FULL_WARPS if in_flight > 1 else 0) if flags is None else flags)
+        pending[k] = i
+        n += 1
+    for j in sorted((p, k) for k, p in enumerate(pending) if p is not None):
+        ctxs[j[1]].sync()
+        if on_frame:
+            on_frame(j[0], bufs[j[1]].array)
+    for c in ctxs:
+        c.close()
+    return n
+
+
+def animation_dims(animation):
+    return animation.height, animation.width
 
 
 _default_ctx = None

@@ -36,6 +36,8 @@ struct DeviceState {
   uint32_t* d_cost = nullptr;                // per-pixel cost of the pre-pass, then the bucket offsets
   uint32_t* d_order = nullptr;               // pixel queue order (most expensive first)
   uint32_t* d_hist = nullptr;                // kCostBuckets counters
+  uint8_t* d_rgb8 = nullptr;                 // packed RGB8 image of tor_render_rgb8
+  size_t rgb8_cap = 0;
   size_t order_cap = 0;                      // pixels
   unsigned long long* d_counters = nullptr;  // [0] primary rays, [1] segments, [2] box-pair tests, [3] exact tests
   bool scene_current = false;
@@ -300,7 +302,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     const unsigned long long lanes = (unsigned long long)grid * block;
     const int32_t pre = spp >= 64 ? (spp >= 256 ? 8 : 4) : 0;
     const bool throughput_bound = total_px >= 4 * lanes;
-    if (total_px < 2 * lanes && total_px > lanes / 2) P.lanes_per_warp = 16;
+    if (total_px < 2 * lanes && total_px > lanes / 2 && !(flags & TOR_FLAG_FULL_WARPS)) P.lanes_per_warp = 16;
     if (const char* e = getenv("TOR_BVH_LANES")) {  // developer tuning knob
       int v = atoi(e);
       P.lanes_per_warp = v < 1 ? 1 : (v > 32 ? 32 : v);
@@ -424,6 +426,7 @@ void tor_ctx_destroy(tor_ctx* ctx) {
     if (d.d_cost) cudaFree(d.d_cost);
     if (d.d_order) cudaFree(d.d_order);
     if (d.d_hist) cudaFree(d.d_hist);
+    if (d.d_rgb8) cudaFree(d.d_rgb8);
     if (d.d_counters) cudaFree(d.d_counters);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
@@ -506,6 +509,55 @@ int tor_render_rows(tor_ctx* ctx, tor_canvas* canvas, const tor_camera* cam, con
                                     cudaMemcpyDeviceToHost, d.stream));
   }
   return tor_sync(ctx);
+}
+
+int tor_render_rgb8_async(tor_ctx* ctx, const tor_canvas* canvas, const tor_camera* cam, const void* objects,
+                          int64_t len, int64_t stride, int64_t max_depth, uint32_t flags, uint8_t* rgb8_out) {
+  if (!ctx) return TOR_ERR_INVALID_ARG;
+  if (!canvas || !rgb8_out) return fail(ctx, TOR_ERR_INVALID_ARG, "canvas or rgb8_out is NULL");
+  const int32_t nrows = canvas->nrows, ncols = canvas->ncols;
+  int rc = check_canvas_dims(ctx, nrows, ncols, canvas->samples_per_pixel, max_depth, 0, nrows, 1);
+  if (rc) return rc;
+  rc = set_scene(ctx, cam, objects, len, stride);
+  if (rc) return rc;
+  DeviceState& d = ctx->devs[0];
+  const size_t npix = (size_t)nrows * ncols;
+  rc = ensure_capacity(ctx, d, device_blob_bytes(ctx), npix * 3 * sizeof(double));
+  if (rc) return rc;
+  if (npix * 3 > d.rgb8_cap) {
+    if (d.d_rgb8) cudaFree(d.d_rgb8);
+    d.d_rgb8 = nullptr;
+    d.rgb8_cap = 0;
+    TOR_CUDA(ctx, cudaMalloc(&d.d_rgb8, npix * 3));
+    d.rgb8_cap = npix * 3;
+  }
+  rc = upload_scene_to(ctx, d);
+  if (rc) return rc;
+  rc = launch_rows(ctx, d, d.d_pixels, nrows, ncols, canvas->samples_per_pixel, canvas->gamma_correction, max_depth,
+                   flags, 0, nrows, 1, d.stream, /*timed=*/true);
+  if (rc) return rc;
+  tor::quantise_rgb8_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, d.stream>>>(d.d_pixels, nrows, ncols, d.d_rgb8);
+  TOR_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  TOR_CUDA(ctx, cudaMemcpyAsync(rgb8_out, d.d_rgb8, npix * 3, cudaMemcpyDeviceToHost, d.stream));
+  return TOR_OK;
+}
+
+int tor_render_rgb8(tor_ctx* ctx, const tor_canvas* canvas, const tor_camera* cam, const void* objects, int64_t len,
+                    int64_t stride, int64_t max_depth, uint32_t flags, uint8_t* rgb8_out) {
+  int rc = tor_render_rgb8_async(ctx, canvas, cam, objects, len, stride, max_depth, flags, rgb8_out);
+  if (rc) return rc;
+  return tor_sync(ctx);
+}
+
+void* tor_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void tor_host_free(void* p) {
+  if (p) cudaFreeHost(p);
 }
 
 int tor_render(tor_ctx* ctx, tor_canvas* canvas, const tor_camera* cam, const void* objects, int64_t len,

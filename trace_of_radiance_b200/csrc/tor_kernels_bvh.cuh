@@ -451,4 +451,22 @@ __global__ void __launch_bounds__(256) draw_kernel(double* __restrict__ pixels, 
   if (i < n) pixels[i] = detmath::pow(inv_spp * pixels[i], inv_gamma);
 }
 
+// io/ppm.nim:14-27 quantisation on the device: int(256 * clamp(c, 0, 0.999)) per channel (NaN -> 0, as the host
+// helper), packed RGB8 in PPM row order (canvas row nrows-1 first).  One thread per pixel of a full canvas.
+__global__ void __launch_bounds__(256) quantise_rgb8_kernel(const double* __restrict__ pixels, int32_t nrows,
+                                                            int32_t ncols, uint8_t* __restrict__ rgb8) {
+  const unsigned long long n = (unsigned long long)nrows * (unsigned long long)ncols;
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t row = (int32_t)(i / (unsigned long long)ncols);
+  const int32_t col = (int32_t)(i - (unsigned long long)row * (unsigned long long)ncols);
+  uint8_t* out = rgb8 + 3ull * ((unsigned long long)(nrows - 1 - row) * (unsigned long long)ncols + col);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double c = pixels[3ull * i + k];
+    const double cl = c < 0.0 ? 0.0 : (c > 0.999 ? 0.999 : c);  // safe_math.nim:10-14
+    out[k] = c != c ? (uint8_t)0 : (uint8_t)(int)(256 * cl);    // ppm.nim:15-16 truncates toward zero
+  }
+}
+
 }  // namespace tor
