@@ -49,6 +49,31 @@ struct BvhRenderParams {
 // One object of a leaf (or of the "always" list) against the ray: the reference's arithmetic
 // (spheres.nim:28-49 / moving_spheres.nim:39-67), operation for operation.  r2 = radius*radius and
 // dc = center1 - center0 were computed on the host with the same IEEE operations.
+// 16-byte loads of the read-only scene data.  For the shared-memory copies the 32-bit shared address is formed once
+// per kernel (a generic pointer costs a window-base computation per access inside the traversal loop).
+template <bool SHARED>
+__device__ __forceinline__ float4 ld16f(const void* generic_base, uint32_t shared_base, int32_t idx16) {
+  if (SHARED) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "r"(shared_base + 16u * (uint32_t)idx16));
+    return v;
+  }
+  return reinterpret_cast<const float4*>(generic_base)[idx16];
+}
+template <bool SHARED>
+__device__ __forceinline__ int4 ld16i(const void* generic_base, uint32_t shared_base, int32_t idx16) {
+  if (SHARED) {
+    int4 v;
+    asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+        : "r"(shared_base + 16u * (uint32_t)idx16));
+    return v;
+  }
+  return reinterpret_cast<const int4*>(generic_base)[idx16];
+}
+
 struct QCache {  // lerp parameter of moving_spheres.nim:41-42, one divide per (time0, time1) per segment
   double t0, t1, q;
 };
@@ -103,6 +128,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
   }
   const float4* __restrict__ nodes = reinterpret_cast<const float4*>((STAGE >= 1 ? smem : P.blob) + bv.off_nodes);
   const double2* __restrict__ recs = reinterpret_cast<const double2*>((STAGE == 2 ? smem : P.blob) + bv.off_objs);
+  const uint32_t nodes_sa = smem_u32(smem) + bv.off_nodes;  // meaningful for STAGE >= 1 only
 
   const double INF = __longlong_as_double(0x7ff0000000000000ll);
   const double t_min = 0.001;  // render.nim:28
@@ -121,11 +147,11 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
   bool active = false, need_pixel = (tid & 31) < P.lanes_per_warp, need_sample = false;
   bool trav_done = false;  // the current segment's closest hit is final
   bool need_setup = false;  // a new segment needs its traversal state
-  unsigned long long seg_count = 0, ray_count = 0, box_count = 0, test_count = 0;
+  unsigned long long seg_count = 0, ray_count = 0;
+  uint32_t box_count = 0, test_count = 0;  // per lane: far below 2^32 (a lane sees ~1e5 segments per render)
 
   // traversal state
-  int32_t stk[kBvhStackDepth];
-  float stk_t[kBvhStackDepth];
+  int2 stk[kBvhStackDepth];  // {child reference, float bits of the entry distance}: one 8-byte local access each
   int sp = 0;
   int32_t cur = 0;
   float idx = 0.f, idy = 0.f, idz = 0.f, oix = 0.f, oiy = 0.f, oiz = 0.f;  // 1/d and o/d in float32
@@ -313,9 +339,10 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
       // ---- inner nodes until a leaf (cur < 0) or the end of the traversal
       if (trav) {
         while (cur >= 0) {
-          const float4* __restrict__ nd = nodes + kNodeStride16 * cur;
-          const float4 n0 = nd[0], n1 = nd[1], n2 = nd[2];
-          const int4 n3 = *reinterpret_cast<const int4*>(nd + 3);
+          const int32_t ni = kNodeStride16 * cur;
+          const float4 n0 = ld16f<(STAGE >= 1)>(nodes, nodes_sa, ni), n1 = ld16f<(STAGE >= 1)>(nodes, nodes_sa, ni + 1),
+                       n2 = ld16f<(STAGE >= 1)>(nodes, nodes_sa, ni + 2);
+          const int4 n3 = ld16i<(STAGE >= 1)>(nodes, nodes_sa, ni + 3);
           ++box_count;
           // child 0: lo = (n0.x, n0.y, n0.z), hi = (n0.w, n1.x, n1.y); child 1: lo = (n1.z, n1.w, n2.x), hi = (n2.y, n2.z, n2.w)
           float ax0 = fmaf(n0.x, idx, -oix), ax1 = fmaf(n0.w, idx, -oix);
@@ -331,8 +358,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
           const bool h0 = near0 <= far0, h1 = near1 <= far1;
           if (h0 && h1) {
             const bool first0 = near0 <= near1;
-            stk[sp] = first0 ? n3.y : n3.x;
-            stk_t[sp] = first0 ? near1 : near0;
+            stk[sp] = make_int2(first0 ? n3.y : n3.x, __float_as_int(first0 ? near1 : near0));
             ++sp;
             cur = first0 ? n3.x : n3.y;
           } else if (h0 || h1) {
@@ -343,8 +369,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
             trav_done = true;
             while (sp > 0) {
               --sp;
-              if (stk_t[sp] <= best_f) {
-                cur = stk[sp];
+              const int2 e = stk[sp];
+              if (__int_as_float(e.y) <= best_f) {
+                cur = e.x;
                 trav_done = false;
                 break;
               }
@@ -369,8 +396,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
         trav_done = true;
         while (sp > 0) {
           --sp;
-          if (stk_t[sp] <= best_f) {
-            cur = stk[sp];
+          const int2 e = stk[sp];
+          if (__int_as_float(e.y) <= best_f) {
+            cur = e.x;
             trav_done = false;
             break;
           }
@@ -381,17 +409,18 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
   }
 
   if (P.count_segments) {
+    unsigned long long box_sum = box_count, test_sum = test_count;
     for (int ofs = 16; ofs > 0; ofs >>= 1) {
       seg_count += __shfl_down_sync(0xffffffffu, seg_count, ofs);
       ray_count += __shfl_down_sync(0xffffffffu, ray_count, ofs);
-      box_count += __shfl_down_sync(0xffffffffu, box_count, ofs);
-      test_count += __shfl_down_sync(0xffffffffu, test_count, ofs);
+      box_sum += __shfl_down_sync(0xffffffffu, box_sum, ofs);
+      test_sum += __shfl_down_sync(0xffffffffu, test_sum, ofs);
     }
     if ((tid & 31) == 0) {
       atomicAdd(P.counters + 0, ray_count);
       atomicAdd(P.counters + 1, seg_count);
-      atomicAdd(P.counters + 2, box_count);
-      atomicAdd(P.counters + 3, test_count);
+      atomicAdd(P.counters + 2, box_sum);
+      atomicAdd(P.counters + 3, test_sum);
     }
   }
 }
