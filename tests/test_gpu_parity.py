@@ -304,3 +304,17 @@ def test_animation_frame_pipeline(tor, oracle):
         cam_arr, objs = an.next_frame(skip=6)
         ref = oracle.render(27, 48, 4, cam_arr, objs, math="det")
         assert np.array_equal(frames[i], oracle.quantise_rgb8(ref)), i
+
+
+def test_multi_device_context(tor, oracle):
+    """tor_ctx_create with several devices: rows interleave over the devices inside one process; same bits."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ctx = tor.Context([0, 1])
+    world, cam = tor.random_scene().list(), _book_cam(tor)
+    _check(tor, oracle, ctx, world, cam, 45, 80, 8)
+    _check(tor, oracle, ctx, world, cam, 45, 80, 8, rows=(3, 44, 5))
+    _check(tor, oracle, ctx, world, cam, 1, 9, 3)  # fewer rows than devices
+    ctx.close()

@@ -1,0 +1,25 @@
+#!/bin/bash
+# compute-sanitizer memcheck over a small render on both routes + the multi-device context test
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_parity.py -q -k "multi_device" 2>&1 | tail -3
+cat > /tmp/san.py <<'PY'
+import sys, os
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import numpy as np
+import trace_of_radiance_b200 as T
+ctx = T.Context()
+world = T.random_scene().list()
+cam = T.camera((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 16.0 / 9.0, 0.1, 10.0, 0.0, 1.0)
+for fl in (0, T.api.TOR_FLAG_BRUTE_FORCE, T.api.TOR_FLAG_ROW_MAJOR_QUEUE):
+    cv = T.newCanvas(24, 40, 64, 2.2)
+    ctx.render(cv, cam, world, 50, flags=fl | T.api.TOR_FLAG_COUNT_SEGMENTS)
+    print(fl, ctx.counters(), float(cv.pixels.sum()))
+big = T.random_scene(0xFACADE, 50).list()
+cv = T.newCanvas(12, 20, 4, 2.2)
+ctx.render(cv, cam, big, 50)
+print("rgb8", ctx.render_rgb8(cv, cam, world, 50).sum())
+PY
+compute-sanitizer --tool memcheck --error-exitcode 3 python /tmp/san.py > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"
+tail -6 gpurun_out/sanitizer_memcheck.log
+compute-sanitizer --tool racecheck --error-exitcode 3 python /tmp/san.py > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"
+tail -4 gpurun_out/sanitizer_racecheck.log

@@ -39,7 +39,6 @@ TOR_SPHERE, TOR_MOVING_SPHERE = 0, 1
 TOR_LAMBERTIAN, TOR_METAL, TOR_DIELECTRIC = 0, 1, 2
 TOR_FLAG_COUNT_SEGMENTS = 0x100
 TOR_FLAG_ROW_MAJOR_QUEUE = 0x400  # BVH route without the longest-pixel-first pre-pass (same image)
-TOR_FLAG_FULL_WARPS = 0x800  # all 32 lanes of a warp take pixels even for small renders (throughput over latency)
 TOR_FLAG_BRUTE_FORCE = 0x200  # scan every object like hittables_lists.nim:48-55 instead of the BVH (same image)
 
 EXPORTED_SYMBOLS = [
@@ -451,8 +450,7 @@ def render_animation(animation, samples_per_pixel=100, max_depth=50, gamma_corre
             ctxs[k].sync()
             if on_frame:
                 on_frame(pending[k], bufs[k].array)
-        ctxs[k].render_rgb8(canvas, cam, world, max_depth, out=bufs[k].array, wait=False,
-                            flags=(TOR_FLAG_FULL_WARPS if in_flight > 1 else 0) if flags is None else flags)
+        ctxs[k].render_rgb8(canvas, cam, world, max_depth, out=bufs[k].array, wait=False, flags=flags or 0)
         pending[k] = i
         n += 1
     for j in sorted((p, k) for k, p in enumerate(pending) if p is not None):

@@ -297,12 +297,26 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     // Scheduling regime, from the number of pixels each lane will get (measured on B200):
     //  * >= 4 pixels per lane: throughput-bound.  Longest-pixel-first queue order (tor_kernels_bvh.cuh): the
     //    pre-pass renders the first `pre` samples of every pixel and keeps only their segment counts.
-    //  * < 2 pixels per lane: bound by the slowest pixel (a serial chain of spp * depth segments).  A lane advances
-    //    faster in a half-populated warp, so only 16 lanes per warp take pixels.
+    //  * fewer: bound by the slowest pixels (each a serial chain of spp * depth segments).  The queue order is
+    //    scrambled so that neighbouring (similarly expensive) pixels land in different warps.
     const unsigned long long lanes = (unsigned long long)grid * block;
     const int32_t pre = spp >= 64 ? (spp >= 256 ? 8 : 4) : 0;
     const bool throughput_bound = total_px >= 4 * lanes;
-    if (total_px < 2 * lanes && total_px > lanes / 2 && !(flags & TOR_FLAG_FULL_WARPS)) P.lanes_per_warp = 16;
+    if (!throughput_bound && !(flags & TOR_FLAG_ROW_MAJOR_QUEUE) && total_px > 64 && total_px < 0xffffffffull &&
+        !getenv("TOR_BVH_NO_SCRAMBLE")) {
+      // latency-bound: scatter the image over the warps (see BvhRenderParams::scramble)
+      unsigned long long m = (unsigned long long)(0.6180339887 * (double)total_px) | 1ull;
+      auto gcd = [](unsigned long long a, unsigned long long b) {
+        while (b) {
+          unsigned long long t = a % b;
+          a = b;
+          b = t;
+        }
+        return a;
+      };
+      while (gcd(m, total_px) != 1) m += 2;
+      P.scramble = (uint32_t)(m % total_px);
+    }
     if (const char* e = getenv("TOR_BVH_LANES")) {  // developer tuning knob
       int v = atoi(e);
       P.lanes_per_warp = v < 1 ? 1 : (v > 32 ? 32 : v);

@@ -41,6 +41,10 @@ struct BvhRenderParams {
   // number of bounce segments the pixel's first `spp` samples took.
   const uint32_t* order;
   uint32_t* cost;
+  // order == NULL and scramble != 0: queue slot i is pixel (i * scramble) mod total (scramble coprime to total): lanes
+  // of a warp get pixels from all over the image, so the few expensive pixels of a latency-bound render end up in
+  // different warps and each runs in a nearly idle warp once its cheap neighbours are done.
+  uint32_t scramble;
   // Lanes of each warp that take pixels (1..32).  With few pixels per lane the render is bound by its slowest
   // pixel, and a lane advances faster in a sparsely populated warp; the host picks the value (tor_api.cu).
   int32_t lanes_per_warp;
@@ -257,7 +261,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
       for (;;) {
         const unsigned long long slot = atomicAdd(P.work_counter, 1ull);
         if (slot >= total_px) break;
-        pid = P.order ? P.order[slot] : (uint32_t)slot;
+        pid = P.order ? P.order[slot]
+                      : (P.scramble ? (uint32_t)((slot * (unsigned long long)P.scramble) % total_px) : (uint32_t)slot);
         pix_seg = 0;
         if (P.spp > 0) {
           int32_t ri = (int32_t)(pid / (uint32_t)P.ncols);
