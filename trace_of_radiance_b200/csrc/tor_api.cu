@@ -142,6 +142,23 @@ int bvh_refill() {
   return v;
 }
 
+// A multiplier m coprime to n with m/n near the golden ratio: i -> i*m mod n is a bijection of [0, n) that sends
+// neighbours far apart.
+uint32_t coprime_near_golden(uint32_t n) {
+  if (n < 3) return 1;
+  unsigned long long m = (unsigned long long)(0.6180339887 * (double)n) | 1ull;
+  auto gcd = [](unsigned long long a, unsigned long long b) {
+    while (b) {
+      unsigned long long t = a % b;
+      a = b;
+      b = t;
+    }
+    return a;
+  };
+  while (gcd(m, n) != 1) m += 2;
+  return (uint32_t)(m % n);
+}
+
 size_t device_blob_bytes(const tor_ctx* ctx) { return ctx->bvh_off + ctx->bvh.blob.size(); }
 
 int ensure_capacity(tor_ctx* ctx, DeviceState& d, size_t blob_bytes, size_t pix_bytes) {
@@ -305,17 +322,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     if (!throughput_bound && !(flags & TOR_FLAG_ROW_MAJOR_QUEUE) && total_px > 64 && total_px < 0xffffffffull &&
         !getenv("TOR_BVH_NO_SCRAMBLE")) {
       // latency-bound: scatter the image over the warps (see BvhRenderParams::scramble)
-      unsigned long long m = (unsigned long long)(0.6180339887 * (double)total_px) | 1ull;
-      auto gcd = [](unsigned long long a, unsigned long long b) {
-        while (b) {
-          unsigned long long t = a % b;
-          a = b;
-          b = t;
-        }
-        return a;
-      };
-      while (gcd(m, total_px) != 1) m += 2;
-      P.scramble = (uint32_t)(m % total_px);
+      P.scramble = coprime_near_golden((uint32_t)total_px);
     }
     if (const char* e = getenv("TOR_BVH_LANES")) {  // developer tuning knob
       int v = atoi(e);
