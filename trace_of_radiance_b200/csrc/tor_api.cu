@@ -311,52 +311,63 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     int grid = (int)(want_b < cap ? want_b : cap);
     if (timed) TOR_CUDA(ctx, cudaEventRecord(d.ev0, stream));
 
-    // Scheduling regime, from the number of pixels each lane will get (measured on B200):
-    //  * >= 4 pixels per lane: throughput-bound.  Longest-pixel-first queue order (tor_kernels_bvh.cuh): the
-    //    pre-pass renders the first `pre` samples of every pixel and keeps only their segment counts.
-    //  * fewer: bound by the slowest pixels (each a serial chain of spp * depth segments).  The queue order is
-    //    scrambled so that neighbouring (similarly expensive) pixels land in different warps.
+    // Pixel scheduling.  A pixel's samples are a serial chain, so the order in which pixels start
+    // decides when the render ends.  With enough samples per pixel a cost pre-pass (the first `pre` samples of every
+    // pixel, only their segment counts kept) ranks the pixels; the most expensive ones are dealt to the lanes so that
+    // every warp starts with the same mix of costs, the rest is queued most-expensive-first.
     const unsigned long long lanes = (unsigned long long)grid * block;
-    const int32_t pre = spp >= 64 ? (spp >= 256 ? 8 : 4) : 0;
-    const bool throughput_bound = total_px >= 4 * lanes;
-    if (!throughput_bound && !(flags & TOR_FLAG_ROW_MAJOR_QUEUE) && total_px > 64 && total_px < 0xffffffffull &&
-        !getenv("TOR_BVH_NO_SCRAMBLE")) {
-      // latency-bound: scatter the image over the warps (see BvhRenderParams::scramble)
-      P.scramble = coprime_near_golden((uint32_t)total_px);
-    }
+    const int32_t pre = spp >= 256 ? 8 : 0;  // below that the pre-pass costs more than the order gains (C1: +1 ms)
+    const bool reorder = !(flags & TOR_FLAG_ROW_MAJOR_QUEUE) && total_px > 64 && total_px < 0x7fffffffull &&
+                         max_depth > 0;
     if (const char* e = getenv("TOR_BVH_LANES")) {  // developer tuning knob
       int v = atoi(e);
       P.lanes_per_warp = v < 1 ? 1 : (v > 32 ? 32 : v);
     }
     if (P.refill > (P.lanes_per_warp * 5) / 8) P.refill = (P.lanes_per_warp * 5) / 8;
     if (P.refill < 1) P.refill = 1;
-    if (pre > 0 && throughput_bound && !(flags & TOR_FLAG_ROW_MAJOR_QUEUE) && total_px < 0xffffffffull &&
-        max_depth > 0) {
-      if (total_px > d.order_cap) {
+    if (reorder && pre > 0 && P.lanes_per_warp == 32 && (block % 32) == 0) {
+      const uint32_t warps = (uint32_t)(lanes / 32);
+      const uint32_t first_wave = warps * 32u;
+      const uint32_t n = (uint32_t)total_px;
+      const uint32_t n_first = n < first_wave ? n : first_wave;
+      const size_t slots = (size_t)first_wave + (n - n_first);
+      if (slots > d.order_cap) {
         if (d.d_cost) cudaFree(d.d_cost);
         if (d.d_order) cudaFree(d.d_order);
         d.d_cost = d.d_order = nullptr;
         d.order_cap = 0;
-        TOR_CUDA(ctx, cudaMalloc(&d.d_cost, total_px * sizeof(uint32_t)));
-        TOR_CUDA(ctx, cudaMalloc(&d.d_order, total_px * sizeof(uint32_t)));
-        d.order_cap = total_px;
+        TOR_CUDA(ctx, cudaMalloc(&d.d_cost, slots * sizeof(uint32_t)));
+        TOR_CUDA(ctx, cudaMalloc(&d.d_order, slots * sizeof(uint32_t)));
+        d.order_cap = slots;
       }
       tor::BvhRenderParams Q = P;
       Q.spp = pre;
       Q.count_segments = 0;
       Q.work_counter = d.d_work + 1;
       Q.cost = d.d_cost;
+      Q.scramble = coprime_near_golden(n);
       plan.fn<<<grid, block, plan.smem, stream>>>(Q);
       TOR_CUDA(ctx, cudaGetLastError());
       TOR_CUDA(ctx, cudaMemsetAsync(d.d_hist, 0, tor::kCostBuckets * sizeof(uint32_t), stream));
-      const uint32_t n = (uint32_t)total_px;
+      TOR_CUDA(ctx, cudaMemsetAsync(d.d_order, 0xff, (size_t)first_wave * sizeof(uint32_t), stream));
       const int sort_grid = (int)((n + 255) / 256 < (unsigned)(d.sm_count * 8) ? (n + 255) / 256 : d.sm_count * 8);
+      static const uint32_t group = [] {  // developer tuning knob: lanes per cost tier
+        const char* e = getenv("TOR_BVH_DEAL_GROUP");
+        int g = e ? atoi(e) : 8;
+        return (uint32_t)((g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) ? g : 8);
+      }();
       tor::cost_histogram_kernel<<<sort_grid, 256, 0, stream>>>(d.d_cost, n, d.d_hist);
       tor::cost_offsets_kernel<<<1, tor::kCostBuckets, 0, stream>>>(d.d_hist);
-      tor::cost_scatter_kernel<<<sort_grid, 256, 0, stream>>>(d.d_cost, n, d.d_hist, d.d_order);
+      tor::cost_scatter_kernel<<<sort_grid, 256, 0, stream>>>(d.d_cost, n, d.d_hist, d.d_order, warps, group, n_first);
       TOR_CUDA(ctx, cudaGetLastError());
       ctx->launches += 4;
       P.order = d.d_order;
+      P.first_wave = first_wave;
+      P.total_slots = (uint32_t)slots;
+    } else if (reorder && !getenv("TOR_BVH_NO_SCRAMBLE")) {
+      // no cost information (few samples per pixel): scatter the image over the warps so that expensive neighbours
+      // do not share one (BvhRenderParams::scramble)
+      P.scramble = coprime_near_golden((uint32_t)total_px);
     }
     plan.fn<<<grid, block, plan.smem, stream>>>(P);
     TOR_CUDA(ctx, cudaGetLastError());

@@ -45,6 +45,12 @@ struct BvhRenderParams {
   // of a warp get pixels from all over the image, so the few expensive pixels of a latency-bound render end up in
   // different warps and each runs in a nearly idle warp once its cheap neighbours are done.
   uint32_t scramble;
+  // order != NULL and first_wave != 0: the first first_wave entries of `order` are not queued but dealt: the lane
+  // with global index g starts on order[g] (0xffffffff = nothing).  The queue then serves order[first_wave ..
+  // total_slots).  The host deals the most expensive pixels so that every warp starts with the same mix of costs
+  // (cost_scatter_kernel).
+  uint32_t first_wave;
+  uint32_t total_slots;
   // Lanes of each warp that take pixels (1..32).  With few pixels per lane the render is bound by its slowest
   // pixel, and a lane advances faster in a sparsely populated warp; the host picks the value (tor_api.cu).
   int32_t lanes_per_warp;
@@ -149,6 +155,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
   uint32_t pid = 0;      // pixel index inside the selected rows
   uint32_t pix_seg = 0;  // bounce segments of the current pixel
   bool active = false, need_pixel = (tid & 31) < P.lanes_per_warp, need_sample = false;
+  bool first_fetch = P.first_wave != 0;
   bool trav_done = false;  // the current segment's closest hit is final
   bool need_setup = false;  // a new segment needs its traversal state
   unsigned long long seg_count = 0, ray_count = 0;
@@ -259,10 +266,21 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
       need_pixel = false;
       active = false;
       for (;;) {
-        const unsigned long long slot = atomicAdd(P.work_counter, 1ull);
-        if (slot >= total_px) break;
-        pid = P.order ? P.order[slot]
-                      : (P.scramble ? (uint32_t)((slot * (unsigned long long)P.scramble) % total_px) : (uint32_t)slot);
+        if (first_fetch) {  // dealt pixel of this lane, if any
+          first_fetch = false;
+          const uint32_t gid = blockIdx.x * BLOCK + tid;
+          pid = gid < P.first_wave ? P.order[gid] : 0xffffffffu;
+          if (pid == 0xffffffffu) continue;
+        } else if (P.first_wave) {
+          const unsigned long long slot = P.first_wave + atomicAdd(P.work_counter, 1ull);
+          if (slot >= P.total_slots) break;
+          pid = P.order[slot];
+        } else {
+          const unsigned long long slot = atomicAdd(P.work_counter, 1ull);
+          if (slot >= total_px) break;
+          pid = P.order ? P.order[slot]
+                        : (P.scramble ? (uint32_t)((slot * (unsigned long long)P.scramble) % total_px) : (uint32_t)slot);
+        }
         pix_seg = 0;
         if (P.spp > 0) {
           int32_t ri = (int32_t)(pid / (uint32_t)P.ncols);
@@ -467,12 +485,27 @@ __global__ void __launch_bounds__(kCostBuckets) cost_offsets_kernel(uint32_t* __
   hist[b] = s[t] - hist[b];  // exclusive
 }
 
+// pos = rank of the pixel, most expensive first.  The first n_first ranks are dealt to the lanes like cards, in tiers
+// of `group` lanes: ranks 0 .. warps*group-1 go to lanes 0..group-1 of the warps (rank q -> warp q mod warps), the next
+// warps*group ranks to lanes group..2*group-1, and so on.  Every warp starts with the same mix of costs, equally
+// expensive pixels sit in neighbouring lanes of the same tier, and the ranks after the first wave are queued in order.
 __global__ void __launch_bounds__(256) cost_scatter_kernel(const uint32_t* __restrict__ cost, uint32_t n,
-                                                           uint32_t* __restrict__ offsets, uint32_t* __restrict__ order) {
+                                                           uint32_t* __restrict__ offsets, uint32_t* __restrict__ order,
+                                                           uint32_t warps, uint32_t group, uint32_t n_first) {
+  const uint32_t first_wave = warps * 32u, tier = warps * group;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint32_t c = cost[i];
     uint32_t pos = atomicAdd(&offsets[c < kCostBuckets ? c : kCostBuckets - 1], 1u);
-    order[pos] = i;
+    uint32_t slot;
+    if (warps == 0) {
+      slot = pos;
+    } else if (pos < n_first) {
+      const uint32_t t = pos / tier, q = pos - t * tier;
+      slot = (q % warps) * 32u + t * group + q / warps;
+    } else {
+      slot = first_wave + (pos - n_first);
+    }
+    order[slot] = i;
   }
 }
 
