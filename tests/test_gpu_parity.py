@@ -318,3 +318,12 @@ def test_multi_device_context(tor, oracle):
     _check(tor, oracle, ctx, world, cam, 45, 80, 8, rows=(3, 44, 5))
     _check(tor, oracle, ctx, world, cam, 1, 9, 3)  # fewer rows than devices
     ctx.close()
+
+
+@pytest.mark.parametrize("h,w,spp,rows", [(20, 30, 256, None), (45, 80, 300, None), (45, 80, 256, (1, 45, 4)),
+                                           (3, 700, 256, None), (90, 160, 256, None)])
+def test_cost_ranked_pixel_queue(tor, oracle, gpu_ctx, h, w, spp, rows):
+    """spp >= 256 turns on the cost pre-pass + dealt / longest-first pixel queue (tor_api.cu): canvases with fewer
+    pixels than lanes, pixel counts that are not a multiple of the CTA size, row subsets, and more pixels than one
+    CTA wave."""
+    _check(tor, oracle, gpu_ctx, tor.random_scene().list(), _book_cam(tor), h, w, spp, rows=rows)

@@ -13,10 +13,11 @@
 //   S  "shade": lanes whose traversal has finished shade the hit / the sky, start the next segment,
 //      sample or pixel (pixels come from a global atomic queue) and set up the next traversal;
 //   T  "traverse": while-while traversal (inner nodes until a leaf, then the leaf's spheres), which
-//      keeps running until at least kRefill lanes of the warp wait for phase S (or nobody traverses).
+//      keeps running until at least `refill` lanes of the warp wait for phase S (or nobody traverses).
 // A lane keeps its traversal state (node, stack, closest hit) across phase S of its neighbours, so the
 // expensive float64 shading code (sincos, sqrt, divides) always runs with many lanes, and the
-// traversal loop always with at least 32 - kRefill.
+// traversal loop always with at least 32 - refill.  The warp re-converges explicitly (__syncwarp) between
+// the steps: left to itself the compiler's schedule ran the sphere test at 2 lanes per instruction.
 #pragma once
 #include "tor_bvh.hpp"
 #include "tor_kernels.cuh"
@@ -35,7 +36,7 @@ struct BvhRenderParams {
   uint32_t count_segments;
   unsigned long long* work_counter;
   unsigned long long* counters;  // [0] primary rays, [1] segments, [2] box-pair tests, [3] exact sphere tests
-  int32_t refill;                // waiting lanes of a warp that trigger a shade phase (kRefill in the text above)
+  int32_t refill;                // waiting lanes of a warp that trigger a shade phase
   // Pixel scheduling.  order == NULL: queue slot i is pixel i (row-major over the selected rows); otherwise pixel
   // order[i].  cost != NULL marks the cost pre-pass: nothing is written to `pixels`, cost[pixel] receives the
   // number of bounce segments the pixel's first `spp` samples took.
@@ -51,8 +52,7 @@ struct BvhRenderParams {
   // (cost_scatter_kernel).
   uint32_t first_wave;
   uint32_t total_slots;
-  // Lanes of each warp that take pixels (1..32).  With few pixels per lane the render is bound by its slowest
-  // pixel, and a lane advances faster in a sparsely populated warp; the host picks the value (tor_api.cu).
+  // Lanes of each warp that take pixels (1..32; 32 unless the TOR_BVH_LANES tuning knob says otherwise).
   int32_t lanes_per_warp;
 };
 
