@@ -9,6 +9,6 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.jso
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 grep -c render_bvh gpurun_out/launches.csv
-ncu --set full --clock-control none --import-source on -k regex:render_bvh -s 3 -c 1 -f -o gpurun_out/prof_bvh_r01f \
+ncu --set full --clock-control none --import-source on -k regex:render_bvh -s 1 -c 1 -f -o gpurun_out/prof_bvh_r01f \
     python tools/sweep.py --dims 450 800 128 2 > gpurun_out/ncu_bvh_r01f.log 2>&1
 tail -2 gpurun_out/ncu_bvh_r01f.log
