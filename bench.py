@@ -46,6 +46,23 @@ def ncu_traffic(kernel):
     return None
 
 
+def ncu_pipe_summary():
+    """FP64 pipe / issue / SIMD utilisation of the render kernel from the committed `ncu --set full` capture
+    (profiles/r01f_ncu_bvh_800x450x128.json: same scene and camera at 800x450 / 128 spp); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r01f_ncu_bvh_800x450x128.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))[0]
+
+    def v(k):
+        return d.get(k, {}).get("value")
+
+    return {"fp64_pipe_active_pct": v("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+            "issue_active_pct": v("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "active_lanes_per_instruction": v("smsp__thread_inst_executed_per_inst_executed.ratio"),
+            "source": "profiles/r01f_ncu_bvh_800x450x128.json (captured under ncu, not a timing)"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -323,6 +340,7 @@ def _run_ours_on_stream(args, wl, rank, world_size, local_rank, dev, torch, dist
                                   "measured_dfma_per_s": fp64_peak, "route": args.route,
                                   "bvh_node_visits_per_step": cnt.get("bvh_node_visits"),
                                   "bvh_sphere_tests_per_step": cnt.get("bvh_sphere_tests"),
+                                  "ncu": ncu_pipe_summary() if args.route == "bvh" else None,
                                   "reference_flop_per_test": 32.8,
                                   "reference_equivalent_flop_per_s": tests_per_s * 32.8}},
         }
