@@ -89,3 +89,51 @@ def test_uninterleave():
     full = D.uninterleave(g, nrows)
     assert full.shape == (nrows, 2, 3)
     assert all((full[r] == r).all() for r in range(nrows))
+
+
+def _anim_worker(rank, world, port, nframes, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    import trace_of_radiance_b200 as T
+    from trace_of_radiance_b200 import distributed as D
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def render_frame(cam, world_list):  # the oracle stands in for the GPU render on this CPU-only test
+            img = O.render(9, 16, 2, cam.as_array(), world_list.objects, math="det", nthreads=2)
+            return O.quantise_rgb8(img)
+
+        frames = D.render_animation_distributed(lambda: T.Animation(height=9, width=16, t_max=9.0), render_frame,
+                                                nframes, (9, 16, 3))
+        q.put((rank, frames.numpy().tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nframes", [(2, 5), (3, 4)])
+def test_animation_frames_are_dealt_to_ranks_and_gathered(world, nframes):
+    """scenes_animated.nim frames f -> rank f mod G, one all_gather; equals the single-process frame sequence."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_anim_worker, args=(r, world, port, nframes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    an = O.Animation(height=9, width=16, t_max=9.0)
+    want = []
+    for _ in range(nframes):
+        cam, objs = an.next_frame(skip=6)
+        want.append(O.quantise_rgb8(O.render(9, 16, 2, cam, objs, math="det", nthreads=2)))
+    want = np.stack(want).tobytes()
+    for rank, b in got:
+        assert b == want, f"rank {rank}"

@@ -88,3 +88,43 @@ class DistributedRenderer:
         host = torch.from_numpy(canvas.pixels)
         host.copy_(img, non_blocking=False)
         return canvas
+
+
+# ------------------------------------------------------------------------------------ animation
+def frames_of_rank(nframes, rank, world):
+    """Frame f goes to rank f mod G (frames are the independent unit of the animation)."""
+    return list(range(rank, nframes, world))
+
+
+def frames_per_rank(nframes, world):
+    return (nframes + world - 1) // world
+
+
+def gather_frames(local, nframes, group=None):
+    """local: (frames_per_rank, h, w, 3) uint8 on every rank, frame f of this rank at slot f div G (the tail slot
+    is padding on ranks that own one frame fewer).  Returns (nframes, h, w, 3) on every rank.  One collective."""
+    world = dist.get_world_size(group)
+    fpr = frames_per_rank(nframes, world)
+    assert local.shape[0] == fpr
+    gathered = torch.empty((world * fpr,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, local.contiguous(), group=group)
+    return uninterleave(gathered.view((world, fpr) + tuple(local.shape[1:])), nframes)
+
+
+def render_animation_distributed(make_animation, render_frame, nframes, frame_shape, skip=6, device=None, group=None):
+    """The frame loop of trace_of_radiance_animation.nim:173-199 across ranks.  Every rank steps the (cheap,
+    deterministic) animation itself and renders only its frames f = rank mod G; ONE all_gather assembles the
+    RGB8 frames.  make_animation() -> object with .scenes(skip) (tor.Animation); render_frame(cam, world) -> (h, w, 3)
+    uint8 array (e.g. ctx.render_rgb8).  Returns a (nframes, h, w, 3) uint8 tensor on every rank."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    fpr = frames_per_rank(nframes, world)
+    local = torch.zeros((fpr,) + tuple(frame_shape), dtype=torch.uint8, device=device or "cpu")
+    for f, (cam, scene) in enumerate(make_animation().scenes(skip=skip)):
+        if f >= nframes:
+            break
+        if f % world == rank:
+            local[f // world] = torch.as_tensor(render_frame(cam, scene)).to(local.device)
+    if world == 1:
+        return local[:nframes]
+    return gather_frames(local, nframes, group=group)
