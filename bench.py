@@ -231,6 +231,8 @@ def _run_ours_on_stream(args, wl, rank, world_size, local_rank, dev, torch, dist
         torch.cuda.synchronize(dev)
 
     route = T.api.TOR_FLAG_BRUTE_FORCE if args.route == "brute" else 0
+    if args.mode == "fast":
+        route |= T.api.TOR_MODE_FAST
 
     def step():
         return R.render_device(nrows, ncols, spp, GAMMA, depth, flags=route)
@@ -311,6 +313,32 @@ def _run_ours_on_stream(args, wl, rank, world_size, local_rank, dev, torch, dist
     n_obj = len(scene)
     tests_per_s = segments * n_obj / (dev_ms / args.steps * 1e-3)
 
+    # ---- split-stream mode (TOR_MODE_FAST) beside the headline: same workload, same float64 arithmetic, the pixel's
+    #      sample loop cut into RNG substreams (deterministic, bit-exact against the oracle's restatement, a different
+    #      Monte-Carlo estimate than the reference's image) — reported, never substituted for `value`
+    split = None
+    if args.mode == "exact" and args.route == "bvh":
+        fl = route | T.api.TOR_MODE_FAST
+        for _ in range(2):
+            R.render_device(nrows, ncols, spp, GAMMA, depth, flags=fl)
+        barrier()
+        fev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in fev:
+            flush.zero_()
+            a.record()
+            R.render_device(nrows, ncols, spp, GAMMA, depth, flags=fl)
+            b.record()
+            b.synchronize()
+        barrier()
+        ft = torch.tensor([sum(a.elapsed_time(b) for a, b in fev)], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+        fms = float(ft[0]) / args.steps
+        split = {"value": rays_per_step / (fms * 1e-3) / 1e6, "unit": "Mray/s", "ms_per_step": fms,
+                 "flags": "TOR_MODE_FAST (automatic substream count: 2^24 / pixels, <= spp, <= 32)",
+                 "parity": "bit-exact vs the oracle's render_split; vs the reference image: within 4*sqrt(2)*sigma/"
+                           "sqrt(spp) per pixel (tests/test_split_stream.py)"}
+
     if rank == 0:
         base = cpu_baseline(wl, args.cpu_seconds) if (world_size == 1 and not args.no_cpu_baseline) else None
         line = {
@@ -318,7 +346,9 @@ def _run_ours_on_stream(args, wl, rank, world_size, local_rank, dev, torch, dist
             "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: random_scene(seed 0xFACADE, {n_obj} objects) {ncols}x{nrows} / "
-                                   f"{spp} spp / depth {depth}, gamma float32(2.2), exact mode (bit-identical image)",
+                                   f"{spp} spp / depth {depth}, gamma float32(2.2), " +
+                                   ("exact mode (bit-identical image)" if args.mode == "exact" else
+                                    "split-stream mode (TOR_MODE_FAST)"),
                        "partition": f"rows interleaved over {world_size} rank(s) + one all_gather",
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)",
                        "wall_s_timed_region": t_wall},
@@ -344,6 +374,8 @@ def _run_ours_on_stream(args, wl, rank, world_size, local_rank, dev, torch, dist
                                   "reference_flop_per_test": 32.8,
                                   "reference_equivalent_flop_per_s": tests_per_s * 32.8}},
         }
+        if split:
+            line["split_stream_mode"] = split
         if base:
             line["cpu_baseline"] = base
         print(json.dumps(line), flush=True)
@@ -358,6 +390,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--route", default="bvh", choices=["bvh", "brute"],
                     help="closest-hit search: BVH in front of the reference's sphere test (default) or the full scan")
+    ap.add_argument("--mode", default="exact", choices=["exact", "fast"],
+                    help="exact: the reference's per-pixel RNG stream (bit-identical image; the headline).  fast: "
+                         "TOR_MODE_FAST split-stream mode as the measured arm")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -123,6 +123,34 @@ int oracle_render(double* pixels, int32_t nrows, int32_t ncols, int32_t spp, flo
   return 0;
 }
 
+// Split-stream ("fast") mode of include/tor_b200.h, restated (tor_oracle.hpp render_split).  nsub must be a power
+// of two in 1..64; nsub = 1 is oracle_render.  pixels / linear_sum / sum_sq are optional canvas-sized outputs.
+int oracle_render_split(double* pixels, int32_t nrows, int32_t ncols, int32_t spp, float gamma_correction,
+                        const double* cam24, const Hittable* world, int64_t n, int64_t max_depth, int32_t row_begin,
+                        int32_t row_end, int32_t row_step, int32_t math_mode, int32_t nthreads, uint32_t nsub,
+                        double* linear_sum, double* sum_sq, uint64_t* counters3) {
+  if (!cam24 || !world || n <= 0 || row_step <= 0) return -1;
+  if (nsub < 1 || nsub > 64 || (nsub & (nsub - 1))) return -1;
+  Camera cam;
+  memcpy(&cam, cam24, sizeof(cam));
+  Counters c;
+  int prev = omp_get_max_threads();
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+  if (math_mode == 0)
+    render_split<LibmMath>(pixels, nrows, ncols, spp, gamma_correction, cam, world, n, max_depth, row_begin, row_end,
+                           row_step, nsub, linear_sum, sum_sq, &c);
+  else
+    render_split<DetMath>(pixels, nrows, ncols, spp, gamma_correction, cam, world, n, max_depth, row_begin, row_end,
+                          row_step, nsub, linear_sum, sum_sq, &c);
+  if (nthreads > 0) omp_set_num_threads(prev);
+  if (counters3) {
+    counters3[0] += c.primary_rays;
+    counters3[1] += c.segments;
+    counters3[2] += c.sphere_tests;
+  }
+  return 0;
+}
+
 int32_t oracle_num_threads(void) { return omp_get_max_threads(); }
 
 // --- io/ppm.nim -----------------------------------------------------------------------

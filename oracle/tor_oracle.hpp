@@ -419,6 +419,101 @@ static inline void render_pixel(double* out3, int64_t row, int64_t col, int32_t 
   out3[2] = M::pow_(scale * pixel.z, gamma);
 }
 
+// ---- split-stream ("fast") mode: NOT in the reference.  It is the restatement of what TOR_MODE_FAST of
+// include/tor_b200.h defines, so that the CUDA path can be checked bit for bit in that mode too:
+//   * the pixel's sample loop (render.nim:62-67) is cut into nsub = 2^k consecutive ranges
+//     [floor(j*spp/nsub), floor((j+1)*spp/nsub));
+//   * range j has its own xoshiro256+ state: outputs 4j .. 4j+3 of the SplitMix64 sequence that rng.nim:46-53
+//     starts at pair(row, col) — range 0 is the reference's own stream, and nsub = 1 is the reference's render;
+//   * the per-range sums are added pairwise, lower index on the left: ((s0+s1)+(s2+s3))+...
+static inline void seed_substream(Rng& rng, int64_t row, int64_t col, uint32_t sub) {
+  uint64_t sm = pair(row, col) + (uint64_t)(4u * sub) * 0x9e3779b97f4a7c15ull;  // SplitMix64 advanced 4*sub steps
+  rng.s0 = splitMix64(sm);
+  rng.s1 = splitMix64(sm);
+  rng.s2 = splitMix64(sm);
+  rng.s3 = splitMix64(sm);
+}
+
+// Linear (pre-draw) sum of one pixel in split-stream mode; sq3 (optional) receives the per-channel sum of squares
+// of the sample colours (for the Monte-Carlo standard error the statistical parity test needs).
+template <class M>
+static inline Vec3 pixel_sum_split(int64_t row, int64_t col, int32_t nrows, int32_t ncols, int32_t spp,
+                                   uint32_t nsub, const Camera& cam, const Hittable* world, int64_t n,
+                                   int64_t max_depth, uint64_t& segments, double* sq3) {
+  Vec3 part[64];
+  for (uint32_t j = 0; j < nsub; ++j) {
+    Rng rng;
+    seed_substream(rng, row, col, j);
+    const int32_t s_begin = (int32_t)(((uint64_t)j * (uint64_t)spp) / nsub);
+    const int32_t s_end = (int32_t)(((uint64_t)(j + 1) * (uint64_t)spp) / nsub);
+    Vec3 pixel{0, 0, 0};
+    for (int32_t s = s_begin; s < s_end; ++s) {
+      double u = ((double)col + uniform01(rng)) / (double)(ncols - 1);
+      double v = ((double)row + uniform01(rng)) / (double)(nrows - 1);
+      Ray r = camera_ray(cam, u, v, rng);
+      Vec3 c = radiance<M>(r, world, n, max_depth, rng, segments);
+      pixel.x += c.x;
+      pixel.y += c.y;
+      pixel.z += c.z;
+      if (sq3) {
+        sq3[0] += c.x * c.x;
+        sq3[1] += c.y * c.y;
+        sq3[2] += c.z * c.z;
+      }
+    }
+    part[j] = pixel;
+  }
+  for (uint32_t w = 1; w < nsub; w <<= 1)
+    for (uint32_t j = 0; j + w < nsub; j += 2 * w) part[j] = part[j] + part[j + w];
+  return part[0];
+}
+
+// The split-stream render over the selected rows.  linear_sum (optional, canvas-sized) receives the pre-draw sums,
+// sum_sq (optional) the per-channel sums of squares.
+template <class M>
+static void render_split(double* pixels, int32_t nrows, int32_t ncols, int32_t spp, float gamma_correction,
+                         const Camera& cam, const Hittable* world, int64_t n, int64_t max_depth, int32_t row_begin,
+                         int32_t row_end, int32_t row_step, uint32_t nsub, double* linear_sum, double* sum_sq,
+                         Counters* counters) {
+  uint64_t segments = 0;
+  int64_t nsel = (row_end > row_begin) ? (row_end - row_begin + row_step - 1) / row_step : 0;
+  const double scale = 1.0 / (double)spp;               // canvas.nim:49
+  const double gamma = 1.0 / (double)gamma_correction;  // canvas.nim:50
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : segments) collapse(2)
+  for (int64_t ri = 0; ri < nsel; ++ri) {
+    for (int64_t cb = 0; cb < (ncols + 31) / 32; ++cb) {
+      int64_t row = row_begin + ri * row_step;
+      int64_t cend = (cb + 1) * 32 < ncols ? (cb + 1) * 32 : ncols;
+      for (int64_t col = cb * 32; col < cend; ++col) {
+        const int64_t at = 3 * (row * ncols + col);
+        double sq[3] = {0, 0, 0};
+        Vec3 sum = pixel_sum_split<M>(row, col, nrows, ncols, spp, nsub, cam, world, n, max_depth, segments,
+                                      sum_sq ? sq : nullptr);
+        if (linear_sum) {
+          linear_sum[at] = sum.x;
+          linear_sum[at + 1] = sum.y;
+          linear_sum[at + 2] = sum.z;
+        }
+        if (sum_sq) {
+          sum_sq[at] = sq[0];
+          sum_sq[at + 1] = sq[1];
+          sum_sq[at + 2] = sq[2];
+        }
+        if (pixels) {
+          pixels[at] = M::pow_(scale * sum.x, gamma);
+          pixels[at + 1] = M::pow_(scale * sum.y, gamma);
+          pixels[at + 2] = M::pow_(scale * sum.z, gamma);
+        }
+      }
+    }
+  }
+  if (counters) {
+    counters->primary_rays += (uint64_t)nsel * ncols * spp;
+    counters->segments += segments;
+    counters->sphere_tests += segments * (uint64_t)n;
+  }
+}
+
 // render.nim:49-68 over rows row_begin, row_begin+row_step, ... < row_end.  `pixels` is the
 // full canvas (nrows*ncols*3 doubles, row 0 = bottom); only the selected rows are written.
 template <class M>

@@ -85,6 +85,11 @@ def lib():
         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, u64p,
     ]
     L.oracle_render.restype = C.c_int
+    L.oracle_render_split.argtypes = [
+        dp, C.c_int32, C.c_int32, C.c_int32, C.c_float, dp, C.c_void_p, C.c_int64, C.c_int64,
+        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, dp, dp, u64p,
+    ]
+    L.oracle_render_split.restype = C.c_int
     L.oracle_num_threads.restype = C.c_int32
     L.oracle_quantise_rgb8.argtypes = [dp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
     L.oracle_export_ppm.argtypes = [dp, C.c_int32, C.c_int32, C.c_char_p]
@@ -190,6 +195,28 @@ def render(nrows, ncols, spp, cam, world, max_depth=50, gamma=2.2, rows=None, ma
         counters["segments"] = counters.get("segments", 0) + int(cnt[1])
         counters["sphere_tests"] = counters.get("sphere_tests", 0) + int(cnt[2])
     return out
+
+
+def render_split(nrows, ncols, spp, cam, world, nsub, max_depth=50, gamma=2.2, rows=None, math="det", nthreads=0,
+                 counters=None, stats=False):
+    """The split-stream ("fast") mode of include/tor_b200.h restated on the CPU: nsub substreams per pixel.
+    Returns the drawn canvas, or (canvas, linear_sum, sum_sq) with stats=True."""
+    out = np.zeros((nrows, ncols, 3), dtype=np.float64)
+    lin = np.zeros_like(out) if stats else None
+    sq = np.zeros_like(out) if stats else None
+    rb, re, rs = rows if rows is not None else (0, nrows, 1)
+    world = np.ascontiguousarray(world)
+    cam = np.ascontiguousarray(cam, dtype=np.float64)
+    cnt = (C.c_uint64 * 3)()
+    rc = lib().oracle_render_split(_dp(out), nrows, ncols, spp, gamma, _dp(cam), world.ctypes.data, len(world),
+                                   max_depth, rb, re, rs, 0 if math == "libm" else 1, nthreads, nsub,
+                                   _dp(lin) if stats else None, _dp(sq) if stats else None, cnt)
+    if rc != 0:
+        raise RuntimeError("oracle_render_split failed")
+    if counters is not None:
+        counters["primary_rays"] = counters.get("primary_rays", 0) + int(cnt[0])
+        counters["segments"] = counters.get("segments", 0) + int(cnt[1])
+    return (out, lin, sq) if stats else out
 
 
 def num_threads():

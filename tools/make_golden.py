@@ -5,6 +5,7 @@ container (needs /root/reference); the outputs are committed so nothing reads /r
                                (the reference's own render of random_scene, 384x216) — decoded, not re-rendered.
   c1_oracle_digest.json      : sha256 of the oracle's float64 framebuffer for config C1 in both math modes,
                                plus its deterministic counters (primary rays / segments).
+  c1_split32_digest.json     : the same for the split-stream mode (32 substreams per pixel) and its PSNR against the PNG.
 """
 import hashlib
 import json
@@ -42,6 +43,23 @@ def main():
     with open(os.path.join(GOLD, "c1_oracle_digest.json"), "w") as f:
         json.dump(digest, f, indent=1)
     print(json.dumps(digest, indent=1))
+
+    # split-stream mode (TOR_MODE_FAST) at C1 with 32 sample ranges per pixel: digest of the oracle's restatement and
+    # its distance to the reference's PNG (an independent 100-spp estimate of the same image)
+    cnt = {}
+    img = O.render_split(216, 384, 100, cam, world, 32, math="det", counters=cnt)
+    q = O.quantise_rgb8(img).astype(np.float64)
+    psnr = float(10.0 * np.log10(255.0**2 / np.mean((q - png.astype(np.float64)) ** 2)))
+    split = {
+        "config": digest["config"] + ", TOR_MODE_FAST with 32 substreams",
+        "f64_sha256": hashlib.sha256(img.tobytes()).hexdigest(),
+        "counters": cnt,
+        "psnr_vs_reference_png_db": psnr,
+        "psnr_vs_reference_png_floor_db": float(np.floor(psnr - 0.5)),
+    }
+    with open(os.path.join(GOLD, "c1_split32_digest.json"), "w") as f:
+        json.dump(split, f, indent=1)
+    print(json.dumps(split, indent=1))
 
 
 if __name__ == "__main__":

@@ -37,6 +37,15 @@ assert HITTABLE_DTYPE.itemsize == 112
 
 TOR_SPHERE, TOR_MOVING_SPHERE = 0, 1
 TOR_LAMBERTIAN, TOR_METAL, TOR_DIELECTRIC = 0, 1, 2
+TOR_MODE_EXACT = 0x0
+TOR_MODE_FAST = 0x1  # split-stream mode (include/tor_b200.h): n RNG substreams per pixel, deterministic, float64
+
+
+def TOR_FAST_SUBSTREAMS(n):
+    """Number of sample ranges per pixel for TOR_MODE_FAST (power of two <= 32; 0 = chosen from canvas size and spp)."""
+    return (int(n) & 0xFF) << 16
+
+
 TOR_FLAG_COUNT_SEGMENTS = 0x100
 TOR_FLAG_ROW_MAJOR_QUEUE = 0x400  # BVH route without the longest-pixel-first pre-pass (same image)
 TOR_FLAG_BRUTE_FORCE = 0x200  # scan every object like hittables_lists.nim:48-55 instead of the BVH (same image)
@@ -476,6 +485,6 @@ def default_context():
     return _default_ctx
 
 
-def render(canvas, cam, world, max_depth, ctx=None):
+def render(canvas, cam, world, max_depth, ctx=None, flags=0):
     """render.nim:49 — `canvas.render(cam, world.list(), max_depth)`.  Synchronous."""
-    (ctx or default_context()).render(canvas, cam, world, max_depth)
+    (ctx or default_context()).render(canvas, cam, world, max_depth, flags=flags)

@@ -36,6 +36,8 @@ struct DeviceState {
   uint32_t* d_cost = nullptr;                // per-pixel cost of the pre-pass, then the bucket offsets
   uint32_t* d_order = nullptr;               // pixel queue order (most expensive first)
   uint32_t* d_hist = nullptr;                // kCostBuckets counters
+  double* d_partial = nullptr;               // split-stream mode: one partial sum (3 doubles) per (pixel, range)
+  size_t partial_cap = 0;                    // bytes
   uint8_t* d_rgb8 = nullptr;                 // packed RGB8 image of tor_render_rgb8
   size_t rgb8_cap = 0;
   size_t order_cap = 0;                      // pixels
@@ -233,6 +235,32 @@ int check_canvas_dims(tor_ctx* ctx, int32_t nrows, int32_t ncols, int32_t spp, i
   return TOR_OK;
 }
 
+// TOR_MODE_FAST: number of sample ranges per pixel as log2 (0 = exact mode).  The count depends on the flags and on the
+// FULL canvas only, never on the row selection or the device, so any partition of a canvas gives the same image.
+int substream_log2(tor_ctx* ctx, uint32_t flags, int32_t nrows, int32_t ncols, int32_t spp, uint32_t* out) {
+  *out = 0;
+  if (!(flags & TOR_MODE_FAST)) {
+    if (flags & 0x00ff0000u) return fail(ctx, TOR_ERR_INVALID_ARG, "TOR_FAST_SUBSTREAMS without TOR_MODE_FAST");
+    return TOR_OK;
+  }
+  if (flags & TOR_FLAG_BRUTE_FORCE)
+    return fail(ctx, TOR_ERR_INVALID_ARG, "TOR_MODE_FAST is implemented on the BVH route only");
+  uint32_t n = (flags >> 16) & 0xffu;
+  if (n == 0) {  // auto: about 2^24 work units per canvas, at most one range per sample, at most 32
+    const unsigned long long px = (unsigned long long)nrows * (unsigned long long)ncols;
+    unsigned long long want = px ? (1ull << 24) / px : 1ull;
+    if (want > 32) want = 32;
+    if (want > (unsigned long long)(spp > 0 ? spp : 1)) want = (unsigned long long)(spp > 0 ? spp : 1);
+    n = 1;
+    while (2ull * n <= want) n *= 2;
+  }
+  if (n > 32 || (n & (n - 1))) return fail(ctx, TOR_ERR_INVALID_ARG, "TOR_FAST_SUBSTREAMS must be a power of two <= 32");
+  uint32_t lg = 0;
+  while ((1u << lg) < n) ++lg;
+  *out = lg;
+  return TOR_OK;
+}
+
 // Enqueue one render of rows row_begin, row_begin+row_step, ... < row_end on device `d` into d_out.
 int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int32_t ncols, int32_t spp, float gamma,
                 int64_t max_depth, uint32_t flags, int32_t row_begin, int32_t row_end, int32_t row_step,
@@ -244,6 +272,13 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
 
   const bool count = (flags & TOR_FLAG_COUNT_SEGMENTS) != 0;
   const unsigned long long total_px = (unsigned long long)nsel * (unsigned long long)ncols;
+  uint32_t sub_log2 = 0;
+  {
+    int rc = substream_log2(ctx, flags, nrows, ncols, spp, &sub_log2);
+    if (rc) return rc;
+    if (sub_log2 && (total_px << sub_log2) >= 0xffffffffull)
+      return fail(ctx, TOR_ERR_INVALID_ARG, "TOR_MODE_FAST: more than 2^32 (pixel, range) units in one launch");
+  }
   const unsigned long long want = (total_px + kBlock - 1) / kBlock;
   TOR_CUDA(ctx, cudaMemsetAsync(d.d_work, 0, 2 * sizeof(unsigned long long), stream));
 
@@ -307,7 +342,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     TOR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, block, plan.smem));
     if (per_sm < 1) return fail(ctx, TOR_ERR_CUDA, "render kernel does not fit on an SM");
     unsigned long long cap = (unsigned long long)d.sm_count * (unsigned long long)per_sm;
-    const unsigned long long want_b = (total_px + block - 1) / block;
+    const unsigned long long want_b = ((total_px << sub_log2) + block - 1) / block;
     int grid = (int)(want_b < cap ? want_b : cap);
     if (timed) TOR_CUDA(ctx, cudaEventRecord(d.ev0, stream));
 
@@ -316,7 +351,21 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     // pixel, only their segment counts kept) ranks the pixels; the most expensive ones are dealt to the lanes so that
     // every warp starts with the same mix of costs, the rest is queued most-expensive-first.
     const unsigned long long lanes = (unsigned long long)grid * block;
-    const int32_t pre = spp >= 256 ? 8 : 0;  // below that the pre-pass costs more than the order gains (C1: +1 ms)
+    // below 256 spp the pre-pass costs more than the order gains (C1: +1 ms); split-stream units are short and
+    // plentiful, so they need no ranking either
+    const int32_t pre = (spp >= 256 && sub_log2 == 0) ? 8 : 0;
+    if (sub_log2) {
+      const size_t need = (size_t)(total_px << sub_log2) * 3 * sizeof(double);
+      if (need > d.partial_cap) {
+        if (d.d_partial) cudaFree(d.d_partial);
+        d.d_partial = nullptr;
+        d.partial_cap = 0;
+        TOR_CUDA(ctx, cudaMalloc(&d.d_partial, need));
+        d.partial_cap = need;
+      }
+      P.sub_log2 = sub_log2;
+      P.pixels = d.d_partial;
+    }
     const bool reorder = !(flags & TOR_FLAG_ROW_MAJOR_QUEUE) && total_px > 64 && total_px < 0x7fffffffull &&
                          max_depth > 0;
     if (const char* e = getenv("TOR_BVH_LANES")) {  // developer tuning knob
@@ -371,8 +420,14 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     }
     plan.fn<<<grid, block, plan.smem, stream>>>(P);
     TOR_CUDA(ctx, cudaGetLastError());
-    // canvas.nim:47-54 `draw` over the sums the render kernel left behind
     const unsigned long long nch = total_px * 3ull;
+    if (sub_log2) {  // per-range partial sums -> pixel sums, fixed pairwise order
+      const unsigned long long nthr = nch << sub_log2;
+      tor::substream_reduce_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, stream>>>(d.d_partial, d_out, nch, sub_log2);
+      TOR_CUDA(ctx, cudaGetLastError());
+      ctx->launches += 1;
+    }
+    // canvas.nim:47-54 `draw` over the sums the render kernel left behind
     tor::draw_kernel<<<(unsigned)((nch + 255) / 256), 256, 0, stream>>>(d_out, nch, P.inv_spp, P.inv_gamma);
     ctx->launches += 1;
   }
@@ -459,6 +514,7 @@ void tor_ctx_destroy(tor_ctx* ctx) {
     if (d.d_order) cudaFree(d.d_order);
     if (d.d_hist) cudaFree(d.d_hist);
     if (d.d_rgb8) cudaFree(d.d_rgb8);
+    if (d.d_partial) cudaFree(d.d_partial);
     if (d.d_counters) cudaFree(d.d_counters);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);

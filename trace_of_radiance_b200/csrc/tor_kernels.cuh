@@ -85,8 +85,10 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t& state) {  // rng.nim:31
   r = (r ^ (r >> 27)) * 0xbf58476d1ce4e5b9ull;  // same multiplier twice, as in the reference
   return r ^ (r >> 31);
 }
-__device__ __forceinline__ void rng_seed_pixel(Rng& g, int32_t row, int32_t col) {  // rng.nim:21-29,46-53
-  uint64_t sm = ((uint64_t)(int64_t)row << 32) ^ (uint64_t)(int64_t)col;
+// sub = 0 is the reference's seed(row, col).  Split-stream mode (TOR_MODE_FAST) seeds sample range `sub` of the pixel
+// with outputs 4*sub .. 4*sub+3 of the same SplitMix64 sequence (its state advances by a constant per output).
+__device__ __forceinline__ void rng_seed_pixel(Rng& g, int32_t row, int32_t col, uint32_t sub = 0) {  // rng.nim:21-29,46-53
+  uint64_t sm = (((uint64_t)(int64_t)row << 32) ^ (uint64_t)(int64_t)col) + (uint64_t)(4u * sub) * 0x9e3779b97f4a7c15ull;
   g.s0 = splitmix64(sm);
   g.s1 = splitmix64(sm);
   g.s2 = splitmix64(sm);

@@ -54,6 +54,12 @@ struct BvhRenderParams {
   uint32_t total_slots;
   // Lanes of each warp that take pixels (1..32; 32 unless the TOR_BVH_LANES tuning knob says otherwise).
   int32_t lanes_per_warp;
+  // Split-stream mode (TOR_MODE_FAST, include/tor_b200.h): every pixel's sample loop is cut into 2^sub_log2
+  // consecutive ranges with their own RNG substream, and the unit of work a lane pulls from the queue is one
+  // (pixel, range) pair: unit = pixel << sub_log2 | range.  `pixels` then holds one partial sum per unit
+  // (3 doubles at 3*unit) and substream_reduce_kernel adds them up.  sub_log2 == 0 is the exact mode: the unit is
+  // the pixel and its one stream is the reference's (render.nim:59-67).
+  uint32_t sub_log2;
 };
 
 // One object of a leaf (or of the "always" list) against the ray: the reference's arithmetic
@@ -143,6 +149,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
   const double INF = __longlong_as_double(0x7ff0000000000000ll);
   const double t_min = 0.001;  // render.nim:28
   const unsigned long long total_px = (unsigned long long)P.nsel_rows * (unsigned long long)P.ncols;
+  const unsigned long long total_units = total_px << P.sub_log2;
   const int refill = P.refill;
 
   Lane L;
@@ -152,8 +159,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
   L.d = v3(0, 0, 1);
   L.time = 0.0;
   L.row = L.col = L.sample = L.depth = 0;
-  uint32_t pid = 0;      // pixel index inside the selected rows
-  uint32_t pix_seg = 0;  // bounce segments of the current pixel
+  uint32_t pid = 0;      // work unit: pixel index inside the selected rows (<< sub_log2 | sample range)
+  uint32_t pix_seg = 0;  // bounce segments of the current unit
   bool active = false, need_pixel = (tid & 31) < P.lanes_per_warp, need_sample = false;
   bool first_fetch = P.first_wave != 0;
   bool trav_done = false;  // the current segment's closest hit is final
@@ -277,18 +284,29 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
           pid = P.order[slot];
         } else {
           const unsigned long long slot = atomicAdd(P.work_counter, 1ull);
-          if (slot >= total_px) break;
-          pid = P.order ? P.order[slot]
-                        : (P.scramble ? (uint32_t)((slot * (unsigned long long)P.scramble) % total_px) : (uint32_t)slot);
+          if (slot >= total_units) break;
+          if (P.order) {
+            pid = P.order[slot];
+          } else {
+            // consecutive slots are the sample ranges of one pixel (lanes that fetch together trace similar rays);
+            // the pixels themselves come in row-major or scrambled order
+            const unsigned long long ps = slot >> P.sub_log2;
+            const uint32_t px = P.scramble ? (uint32_t)((ps * (unsigned long long)P.scramble) % total_px) : (uint32_t)ps;
+            pid = (px << P.sub_log2) | ((uint32_t)slot & ((1u << P.sub_log2) - 1u));
+          }
         }
         pix_seg = 0;
-        if (P.spp > 0) {
-          int32_t ri = (int32_t)(pid / (uint32_t)P.ncols);
-          L.col = (int32_t)(pid - (uint32_t)ri * (uint32_t)P.ncols);
+        const uint32_t px = pid >> P.sub_log2, sub = pid & ((1u << P.sub_log2) - 1u);
+        // samples [s_begin, s_end) of the pixel; the whole loop of render.nim:62 when sub_log2 == 0
+        const int32_t s_begin = (int32_t)(((unsigned long long)sub * (unsigned long long)P.spp) >> P.sub_log2);
+        const int32_t s_end = (int32_t)(((unsigned long long)(sub + 1u) * (unsigned long long)P.spp) >> P.sub_log2);
+        if (s_end > s_begin) {
+          int32_t ri = (int32_t)(px / (uint32_t)P.ncols);
+          L.col = (int32_t)(px - (uint32_t)ri * (uint32_t)P.ncols);
           L.row = P.row_begin + ri * P.row_step;
-          rng_seed_pixel(L.rng, L.row, L.col);  // render.nim:59-60
+          rng_seed_pixel(L.rng, L.row, L.col, sub);  // render.nim:59-60
           L.pix = v3(0, 0, 0);
-          L.sample = 0;
+          L.sample = P.spp - (s_end - s_begin);  // counts up to spp
           active = true;
           need_sample = true;
           break;
@@ -507,6 +525,30 @@ __global__ void __launch_bounds__(256) cost_scatter_kernel(const uint32_t* __res
     }
     order[slot] = i;
   }
+}
+
+// Split-stream mode: out[p*3 + ch] = sum over the 2^sub_log2 ranges of partial[(p << sub_log2 | j)*3 + ch], added
+// pairwise with the lower index on the left — ((s0+s1)+(s2+s3))+... — which is exactly what the xor butterfly gives
+// the lowest lane of every group (IEEE addition is commutative, so both partners of a step hold the same bits).
+// One lane per (pixel, channel, range); 32 >> sub_log2 pixel-channels per warp.
+__global__ void __launch_bounds__(256) substream_reduce_kernel(const double* __restrict__ partial,
+                                                               double* __restrict__ out, unsigned long long n_pc,
+                                                               uint32_t sub_log2) {
+  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nsub = 1u << sub_log2;
+  const unsigned long long pc = t >> sub_log2;
+  const uint32_t j = (uint32_t)t & (nsub - 1u);
+  double v = 0.0;
+  if (pc < n_pc) {
+    const unsigned long long p = pc / 3ull;
+    const uint32_t ch = (uint32_t)(pc - p * 3ull);
+    v = partial[((p << sub_log2) + j) * 3ull + ch];
+  }
+  for (uint32_t ofs = 1; ofs < nsub; ofs <<= 1) {
+    const double w = __shfl_xor_sync(0xffffffffu, v, ofs);
+    v = (j & ofs) ? w + v : v + w;
+  }
+  if (pc < n_pc && j == 0) out[pc] = v;
 }
 
 // canvas.nim:47-54 `draw` over the sums the render kernel left in the framebuffer: one thread per channel,
