@@ -1,14 +1,16 @@
 #!/bin/bash
 # Final evidence for the round: parity tests, smoke, bench + reference arm, launch list, full ncu capture.
+# usage: tools/gpu_final.sh <tag>   (artefacts land in gpurun_out/<tag>_*)
+TAG=${1:-r01}
 set -x
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 3000 gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>&1; tail -c 300 gpurun_out/bench_ref.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
-grep -c render_bvh gpurun_out/launches.csv
-ncu --set full --clock-control none --import-source on -k regex:render_bvh -s 1 -c 1 -f -o gpurun_out/prof_bvh_r01f \
-    python tools/sweep.py --dims 450 800 128 2 > gpurun_out/ncu_bvh_r01f.log 2>&1
-tail -2 gpurun_out/ncu_bvh_r01f.log
+python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err; tail -c 3500 gpurun_out/${TAG}_bench_n1.json; tail -3 gpurun_out/${TAG}_bench_n1.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference_arm.json 2>&1; tail -c 300 gpurun_out/${TAG}_bench_reference_arm.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/${TAG}_launches_bench_c2.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
+grep -c render_bvh gpurun_out/${TAG}_launches_bench_c2.csv
+ncu --set full --clock-control none --import-source on -k regex:render_bvh -s 1 -c 1 -f -o gpurun_out/${TAG}_prof_bvh \
+    python tools/sweep.py --dims 450 800 128 2 --rowmajor > gpurun_out/${TAG}_ncu_bvh.log 2>&1
+tail -2 gpurun_out/${TAG}_ncu_bvh.log
