@@ -4,6 +4,7 @@
 #include <stdio.h>
 
 #include "tor_oracle.hpp"
+#include "tor_oracle_video.hpp"
 
 using namespace oracle;
 
@@ -172,6 +173,32 @@ int oracle_export_ppm(const double* pixels, int32_t nrows, int32_t ncols, const 
   fwrite(s.data(), 1, s.size(), f);
   fclose(f);
   return 0;
+}
+
+// --- io/rgb.nim, io/color_conversions.nim, io/h264.nim (tor_oracle_video.hpp) -------------------------
+void oracle_to_rgb_raw(const double* pixels, int32_t nrows, int32_t ncols, int32_t as_written, uint8_t* out) {
+  to_rgb_raw(pixels, nrows, ncols, as_written != 0, out);
+}
+int oracle_rgb_to_ycbcr420(int32_t width, int32_t height, const uint8_t* rgb, uint8_t* Y, uint8_t* U, uint8_t* V) {
+  return rgb_to_ycbcr420(width, height, rgb, Y, U, V) ? 0 : -1;
+}
+void oracle_bt601_coefs(uint8_t* out7) {
+  YCbCrCoefs c = bt601_coefs();
+  out7[0] = c.kr; out7[1] = c.kg; out7[2] = c.kb; out7[3] = c.fb; out7[4] = c.fr; out7[5] = c.y_scale; out7[6] = c.y_min;
+}
+// Both return the number of bytes the stream piece has; they write min(size, cap) bytes.
+int64_t oracle_h264_header(int32_t width, int32_t height, uint8_t* out, int64_t cap) {
+  std::vector<uint8_t> v;
+  h264_header(width, height, v);
+  memcpy(out, v.data(), (size_t)((int64_t)v.size() < cap ? (int64_t)v.size() : cap));
+  return (int64_t)v.size();
+}
+int64_t oracle_h264_frame(int32_t width, int32_t height, const uint8_t* Y, const uint8_t* Cb, const uint8_t* Cr,
+                          uint8_t* out, int64_t cap) {
+  std::vector<uint8_t> v;
+  h264_frame(width, height, Y, Cb, Cr, v);
+  memcpy(out, v.data(), (size_t)((int64_t)v.size() < cap ? (int64_t)v.size() : cap));
+  return (int64_t)v.size();
 }
 
 }  // extern "C"

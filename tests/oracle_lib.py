@@ -50,7 +50,7 @@ def lib():
     src_newer = False
     if os.path.exists(LIB_PATH):
         t = os.path.getmtime(LIB_PATH)
-        for f in ("oracle_capi.cc", "tor_oracle.hpp", "../trace_of_radiance_b200/csrc/tor_detmath.h"):
+        for f in ("oracle_capi.cc", "tor_oracle.hpp", "tor_oracle_video.hpp", "../trace_of_radiance_b200/csrc/tor_detmath.h"):
             p = os.path.join(ORACLE_DIR, f)
             if os.path.exists(p) and os.path.getmtime(p) > t:
                 src_newer = True
@@ -94,6 +94,15 @@ def lib():
     L.oracle_quantise_rgb8.argtypes = [dp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
     L.oracle_export_ppm.argtypes = [dp, C.c_int32, C.c_int32, C.c_char_p]
     L.oracle_export_ppm.restype = C.c_int
+    u8p = C.POINTER(C.c_uint8)
+    L.oracle_to_rgb_raw.argtypes = [dp, C.c_int32, C.c_int32, C.c_int32, u8p]
+    L.oracle_rgb_to_ycbcr420.argtypes = [C.c_int32, C.c_int32, u8p, u8p, u8p, u8p]
+    L.oracle_rgb_to_ycbcr420.restype = C.c_int
+    L.oracle_bt601_coefs.argtypes = [u8p]
+    L.oracle_h264_header.argtypes = [C.c_int32, C.c_int32, u8p, C.c_int64]
+    L.oracle_h264_header.restype = C.c_int64
+    L.oracle_h264_frame.argtypes = [C.c_int32, C.c_int32, u8p, u8p, u8p, u8p, C.c_int64]
+    L.oracle_h264_frame.restype = C.c_int64
     _lib = L
     return L
 
@@ -273,3 +282,53 @@ def det_pow_general(x, y):
 
 def libm_pow(x, y):
     return _pow(lib().oracle_libm_pow, x, y)
+
+
+# ------------------------------------------------------------------ io/rgb.nim, color_conversions.nim, h264.nim
+def _u8p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def to_rgb_raw(pixels, as_written=False):
+    """io/rgb.nim:17-31.  as_written=True keeps the reference's row indexing (one row off, top row undefined -> 0)."""
+    nrows, ncols, _ = pixels.shape
+    pixels = np.ascontiguousarray(pixels, dtype=np.float64)
+    out = np.zeros((nrows, ncols, 3), dtype=np.uint8)
+    lib().oracle_to_rgb_raw(_dp(pixels), nrows, ncols, 1 if as_written else 0, _u8p(out))
+    return out
+
+
+def rgb_to_ycbcr420(rgb):
+    """io/color_conversions.nim:180-252 (BT.601): (h, w, 3) uint8 -> Y (h, w), Cb, Cr (h/2, w/2)."""
+    h, w, _ = rgb.shape
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    y = np.zeros((h, w), dtype=np.uint8)
+    cb = np.zeros(((h + 1) // 2, (w + 1) // 2), dtype=np.uint8)
+    cr = np.zeros_like(cb)
+    if lib().oracle_rgb_to_ycbcr420(w, h, _u8p(rgb), _u8p(y), _u8p(cb), _u8p(cr)) != 0:
+        raise ValueError("width and height must be even (color_conversions.nim:201-202)")
+    return y, cb, cr
+
+
+def bt601_coefs():
+    out = np.zeros(7, dtype=np.uint8)
+    lib().oracle_bt601_coefs(_u8p(out))
+    return dict(zip(("kr", "kg", "kb", "fb", "fr", "y_scale", "y_min"), (int(v) for v in out)))
+
+
+def h264_header(width, height):
+    """io/h264.nim:159-168: SPS + PPS."""
+    buf = np.zeros(64, dtype=np.uint8)
+    n = lib().oracle_h264_header(width, height, _u8p(buf), buf.size)
+    return bytes(buf[:n])
+
+
+def h264_frame(y, cb, cr):
+    """io/h264.nim:249-259: one I_PCM slice."""
+    h, w = y.shape
+    y, cb, cr = (np.ascontiguousarray(a, dtype=np.uint8) for a in (y, cb, cr))
+    cap = 16 + (h // 16) * (w // 16) * 386 + 8
+    buf = np.zeros(cap, dtype=np.uint8)
+    n = lib().oracle_h264_frame(w, h, _u8p(y), _u8p(cb), _u8p(cr), _u8p(buf), cap)
+    assert n <= cap
+    return bytes(buf[:n])

@@ -1,0 +1,314 @@
+"""Video export: io/rgb.nim, io/color_conversions.nim, io/h264.nim, io/mp4.nim.
+
+Integer / byte work, so the bar is bit-exact:
+  * the oracle's colour conversion against the BT.601 known answers its algorithm documents;
+  * the library's H.264 writer against the oracle's restatement of io/h264.nim, byte for byte, and against an
+    independent decoder (FFmpeg through cv2): the decoded luma equals the input plane exactly (I_PCM is lossless);
+  * the library's MP4 file against the REFERENCE's own muxer (minimp4.h compiled into oracle/_ref/ref_mp4mux): same
+    parameter sets, same samples, same timing;
+  * on the GPU: tor_render_ycbcr420 against oracle render -> to_rgb_raw -> rgb_to_ycbcr420.
+"""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_MUX = os.path.join(ROOT, "oracle", "_ref", "ref_mp4mux")
+
+# io/h264.nim:36-39 — the reference's constants, quoted here as the known answers of the stream syntax
+REF_PPS = bytes([0x00, 0x00, 0x00, 0x01, 0x68, 0xCE, 0x38, 0x80])
+REF_SLICE_HEADER = bytes([0x00, 0x00, 0x00, 0x01, 0x05, 0x88, 0x84, 0x21, 0xA0])
+REF_MB_HEADER = bytes([0x0D, 0x00])
+
+
+def _test_frames(h, w, n):
+    yy, xx = np.mgrid[0:h, 0:w]
+    return [np.stack([(xx * 3 + k * 20) % 256, (yy * 4 + k * 10) % 256, ((xx + yy) * 2) % 256], -1).astype(np.uint8)
+            for k in range(n)]
+
+
+def _write_264(tor, oracle, path, frames):
+    h, w, _ = frames[0].shape
+    enc = tor.H264Encoder.init(w, h, path)
+    planes = []
+    for rgb in frames:
+        y, cb, cr = oracle.rgb_to_ycbcr420(rgb)
+        Y, Cb, Cr = enc.getFrameBuffers()
+        Y[:], Cb[:], Cr[:] = y, cb, cr
+        enc.flushFrame()
+        planes.append((y, cb, cr))
+    enc.finish()
+    return planes
+
+
+# ------------------------------------------------------------------------------------------ colour conversion
+def test_bt601_coefficients_and_known_answers(oracle):
+    """color_conversions.nim:104-114,178.  Expected Y'CbCr of the primaries: ITU-R BT.601 studio range
+    (white 235/128/128, black 16/128/128, red 81/90/240, green 145/54/34, blue 41/240/110); the 8-bit fixed-point
+    algorithm truncates, so it lands on or one below the rounded values."""
+    assert oracle.bt601_coefs() == {"kr": 77, "kg": 150, "kb": 29, "fb": 127, "fr": 160, "y_scale": 110, "y_min": 16}
+    expect = {(255, 255, 255): (235, 128, 128), (0, 0, 0): (16, 128, 128), (255, 0, 0): (81, 90, 239),
+              (0, 255, 0): (144, 54, 34), (0, 0, 255): (40, 240, 110)}
+    ideal = {(255, 0, 0): (81, 90, 240), (0, 255, 0): (145, 54, 34), (0, 0, 255): (41, 240, 110)}
+    for rgb, want in expect.items():
+        y, cb, cr = oracle.rgb_to_ycbcr420(np.tile(np.array(rgb, dtype=np.uint8), (2, 2, 1)))
+        assert (int(y[0, 0]), int(cb[0, 0]), int(cr[0, 0])) == want
+        assert (y == y[0, 0]).all()
+        if rgb in ideal:
+            assert all(0 <= i - g <= 1 for g, i in zip(want, ideal[rgb]))
+
+
+def test_ycbcr_subsampling_and_range(oracle):
+    rng = np.random.default_rng(7)
+    rgb = rng.integers(0, 256, (16, 24, 3), dtype=np.uint8)
+    y, cb, cr = oracle.rgb_to_ycbcr420(rgb)
+    assert y.shape == (16, 24) and cb.shape == (8, 12) and cr.shape == (8, 12)
+    assert y.min() >= 16 and y.max() <= 235 and cb.min() >= 1 and cb.max() <= 254
+    # independent restatement with wide Python integers (the reference's uint16 / int16 never overflow here)
+    r, g, b = (rgb[..., k].astype(np.int64) for k in range(3))
+    ty = (77 * r + 150 * g + 29 * b) >> 8
+    assert np.array_equal(y, ((ty * 110) >> 7) + 16)
+    tu = (b - ty).reshape(8, 2, 12, 2).sum(axis=(1, 3))
+    tv = (r - ty).reshape(8, 2, 12, 2).sum(axis=(1, 3))
+    assert np.array_equal(cb, (((tu >> 2) * 127) >> 8) + 128)
+    assert np.array_equal(cr, (((tv >> 2) * 160) >> 8) + 128)
+    assert np.abs((tv >> 2) * 160).max() < 32768  # the reference's int16 product cannot overflow
+    with pytest.raises(ValueError):
+        oracle.rgb_to_ycbcr420(np.zeros((3, 4, 3), dtype=np.uint8))
+
+
+def test_rgb_raw_row_indexing(oracle):
+    """io/rgb.nim:26-31: as written, output row i shows canvas row nrows-i (one row off, row 0 out of bounds)."""
+    px = np.zeros((5, 3, 3))
+    for r in range(5):
+        px[r] = (r + 1) / 10.0
+    fixed = oracle.to_rgb_raw(px)
+    assert np.array_equal(fixed, oracle.quantise_rgb8(px))  # == PPM order
+    assert [int(v) for v in fixed[:, 0, 0]] == [int(256 * (r + 1) / 10.0) for r in (4, 3, 2, 1, 0)]
+    lit = oracle.to_rgb_raw(px, as_written=True)
+    assert (lit[0] == 0).all() and np.array_equal(lit[1:], fixed[:-1])
+
+
+# ------------------------------------------------------------------------------------------------ H.264 stream
+def test_h264_sps_known_answers(oracle):
+    """SPS bit layout for two sizes worked out by hand from h264.nim:102-139 (profile 66, level 10, five ue(0),
+    gaps flag, ue(width/16-1), ue(height/16-1), 1 0 0 0, stop bit)."""
+    assert oracle.h264_header(128, 96) == bytes.fromhex("000000016742000af841a2") + REF_PPS
+    assert oracle.h264_header(256, 144) == bytes.fromhex("000000016742000af8202620") + REF_PPS
+
+
+def test_h264_writer_equals_oracle_and_reference_constants(tor, oracle, tmp_path):
+    path = str(tmp_path / "a.264")
+    frames = _test_frames(48, 64, 3)
+    planes = _write_264(tor, oracle, path, frames)
+    got = open(path, "rb").read()
+    want = oracle.h264_header(64, 48) + b"".join(oracle.h264_frame(*p) for p in planes)
+    assert got == want
+    assert got.count(REF_PPS) == 1 and got.count(REF_SLICE_HEADER) == 3
+    mbs = (48 // 16) * (64 // 16)
+    per_frame = len(REF_SLICE_HEADER) + mbs * 384 + (mbs - 1) * len(REF_MB_HEADER) + 1
+    assert len(got) == len(oracle.h264_header(64, 48)) + 3 * per_frame
+    # video-range samples never contain a zero byte, so the raw PCM data cannot emulate a start code
+    assert all(p.min() > 0 for fr in planes for p in fr)
+
+
+def test_h264_rejects_partial_macroblocks(tor, tmp_path):
+    with pytest.raises(tor.api.TorError):
+        tor.H264Encoder.init(100, 48, str(tmp_path / "x.264"))
+
+
+def test_h264_decodes_losslessly_with_ffmpeg(tor, oracle, tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    path = str(tmp_path / "a.264")
+    frames = _test_frames(48, 64, 4)
+    planes = _write_264(tor, oracle, path, frames)
+    cap = cv2.VideoCapture(path)
+    assert cap.isOpened()
+    cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)  # FFmpeg backend: the raw luma plane
+    n = 0
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        assert np.array_equal(fr.reshape(48, 64), planes[n][0])
+        n += 1
+    assert n == 4
+    cap = cv2.VideoCapture(path)  # and through FFmpeg's own YUV -> BGR: close to the RGB we started from
+    for k in range(4):
+        ok, fr = cap.read()
+        assert ok
+        d = np.abs(fr[..., ::-1].astype(int) - frames[k].astype(int))
+        assert d.mean() < 4.0  # 4:2:0 subsampling + 8-bit fixed point; not a bit-exact path
+
+
+# ---------------------------------------------------------------------------------------------------- MP4
+def _boxes(buf, start=0, end=None):
+    end = len(buf) if end is None else end
+    at = start
+    while at + 8 <= end:
+        size, tag = struct.unpack(">I4s", buf[at:at + 8])
+        hdr = 8
+        if size == 1:
+            size = struct.unpack(">Q", buf[at + 8:at + 16])[0]
+            hdr = 16
+        elif size == 0:
+            size = end - at
+        yield tag.decode("latin1"), at + hdr, at + size
+        at += size
+
+
+def _find(buf, path, start=0, end=None):
+    tag, rest = path[0], path[1:]
+    for t, a, b in _boxes(buf, start, end):
+        if t == tag:
+            return (a, b) if not rest else _find(buf, rest, a, b)
+    raise KeyError(tag)
+
+
+def _mp4_summary(path):
+    buf = open(path, "rb").read()
+    stbl = ["moov", "trak", "mdia", "minf", "stbl"]
+    a, b = _find(buf, ["moov", "trak", "mdia", "mdhd"])
+    timescale, duration = struct.unpack(">II", buf[a + 12:a + 20])
+    a, b = _find(buf, stbl + ["stsz"])
+    _, fixed, count = struct.unpack(">III", buf[a:a + 12])
+    sizes = [fixed] * count if fixed else list(struct.unpack(f">{count}I", buf[a + 12:a + 12 + 4 * count]))
+    a, b = _find(buf, stbl + ["stts"])
+    n = struct.unpack(">I", buf[a + 4:a + 8])[0]
+    stts = [struct.unpack(">II", buf[a + 8 + 8 * i:a + 16 + 8 * i]) for i in range(n)]
+    a, b = _find(buf, stbl + ["stsc"])
+    n = struct.unpack(">I", buf[a + 4:a + 8])[0]
+    stsc = [struct.unpack(">III", buf[a + 8 + 12 * i:a + 20 + 12 * i]) for i in range(n)]
+    try:
+        a, b = _find(buf, stbl + ["stco"])
+        n = struct.unpack(">I", buf[a + 4:a + 8])[0]
+        chunks = list(struct.unpack(f">{n}I", buf[a + 8:a + 8 + 4 * n]))
+    except KeyError:
+        a, b = _find(buf, stbl + ["co64"])
+        n = struct.unpack(">I", buf[a + 4:a + 8])[0]
+        chunks = list(struct.unpack(f">{n}Q", buf[a + 8:a + 8 + 8 * n]))
+    # sample offsets from the chunk table
+    offsets, si = [], 0
+    for ci, off in enumerate(chunks, start=1):
+        per = [e for e in stsc if e[0] <= ci][-1][1]
+        for _ in range(per):
+            if si < len(sizes):
+                offsets.append(off)
+                off += sizes[si]
+                si += 1
+    a, b = _find(buf, stbl + ["stsd"])
+    a, b = _find(buf, ["avc1"], a + 8, b)
+    w, h = struct.unpack(">HH", buf[a + 24:a + 28])
+    a, b = _find(buf, ["avcC"], a + 78, b)
+    nsps = buf[a + 5] & 0x1F
+    at, sps = a + 6, []
+    for _ in range(nsps):
+        ln = struct.unpack(">H", buf[at:at + 2])[0]
+        sps.append(buf[at + 2:at + 2 + ln])
+        at += 2 + ln
+    npps, pps = buf[at], []
+    at += 1
+    for _ in range(npps):
+        ln = struct.unpack(">H", buf[at:at + 2])[0]
+        pps.append(buf[at + 2:at + 2 + ln])
+        at += 2 + ln
+    samples = [buf[o:o + s] for o, s in zip(offsets, sizes)]
+    total = sum(c * d for c, d in stts)
+    return {"timescale": timescale, "duration": duration, "width": w, "height": h, "sps": sps, "pps": pps,
+            "samples": samples, "deltas": [d for c, d in stts for _ in range(c)], "ticks": total,
+            "length_size": (buf[a + 4] & 3) + 1}
+
+
+def test_mp4_equals_the_reference_muxer(tor, oracle, tmp_path):
+    """The same .264 through this library's muxer and through the reference's own C muxer (minimp4.h, built from
+    /root/reference into oracle/_ref by oracle/Makefile, driven exactly like io/mp4.nim:66-160)."""
+    if not os.path.exists(REF_MUX):
+        pytest.skip("oracle/_ref/ref_mp4mux not built (needs /root/reference at build time)")
+    src = str(tmp_path / "a.264")
+    planes = _write_264(tor, oracle, src, _test_frames(48, 64, 5))
+    ours, ref = str(tmp_path / "ours.mp4"), str(tmp_path / "ref.mp4")
+    mux = tor.MP4Muxer().initialize(ours, 64, 48)
+    mux.writeMP4_from(src)
+    mux.close()
+    subprocess.check_call([REF_MUX, src, ref, "64", "48", "30"])
+    a, b = _mp4_summary(ours), _mp4_summary(ref)
+    assert a["sps"] == b["sps"] and a["pps"] == b["pps"]
+    assert a["sps"][0] == oracle.h264_header(64, 48)[4:-8] and a["pps"][0] == REF_PPS[4:]
+    assert (a["width"], a["height"]) == (b["width"], b["height"]) == (64, 48)
+    assert a["length_size"] == b["length_size"] == 4
+    assert a["samples"] == b["samples"] and len(a["samples"]) == 5
+    for s, p in zip(a["samples"], planes):  # length prefix + the slice NAL without its start code
+        nal = oracle.h264_frame(*p)[4:]
+        assert s == struct.pack(">I", len(nal)) + nal
+    # timing: 90000 div 30 ticks per frame (mp4.nim:91); compare in seconds, the two files may pick other timescales
+    assert a["timescale"] == 90000 and a["deltas"] == [3000] * 5
+    assert abs(a["ticks"] / a["timescale"] - b["ticks"] / b["timescale"]) < 1e-9
+
+
+def test_mp4_decodes_with_ffmpeg(tor, oracle, tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    src, dst = str(tmp_path / "a.264"), str(tmp_path / "a.mp4")
+    planes = _write_264(tor, oracle, src, _test_frames(48, 64, 6))
+    mux = tor.MP4Muxer().initialize(dst, 64, 48)
+    mux.writeMP4_from(src)
+    cap = cv2.VideoCapture(dst)
+    assert cap.isOpened()
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 6 and abs(cap.get(cv2.CAP_PROP_FPS) - 30.0) < 1e-6
+    assert (int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))) == (64, 48)
+    cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+    for k in range(6):
+        ok, fr = cap.read()
+        assert ok and np.array_equal(fr.reshape(48, 64), planes[k][0])
+    with pytest.raises(tor.api.TorError):
+        tor.MP4Muxer().initialize(dst, 64, 48).writeMP4_from(str(tmp_path / "missing.264"))
+
+
+# ---------------------------------------------------------------------------------------------------- GPU
+def _book_cam(tor):
+    return tor.camera((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 16.0 / 9.0, 0.1, 10.0, 0.0, 1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("as_written", [False, True])
+def test_gpu_ycbcr420_bit_exact(tor, oracle, gpu_ctx, as_written):
+    world, cam = tor.random_scene().list(), _book_cam(tor)
+    h, w, spp = 36, 64, 6
+    cv = tor.newCanvas(h, w, spp, 2.2)
+    fl = tor.api.TOR_FLAG_RGB_ROWS_AS_WRITTEN if as_written else 0
+    y, cb, cr = gpu_ctx.render_ycbcr420(cv, cam, world, 50, flags=fl)
+    img = oracle.render(h, w, spp, cam.as_array(), world.objects, math="libm")
+    ry, rcb, rcr = oracle.rgb_to_ycbcr420(oracle.to_rgb_raw(img, as_written=as_written))
+    assert np.array_equal(y, ry) and np.array_equal(cb, rcb) and np.array_equal(cr, rcr)
+    odd = tor.newCanvas(35, 64, 1, 2.2)
+    with pytest.raises(tor.api.TorError):
+        gpu_ctx.render_ycbcr420(odd, cam, world, 50)
+
+
+@pytest.mark.gpu
+def test_gpu_animation_to_mp4(tor, oracle, gpu_ctx, tmp_path):
+    """main_animation_mp4 (trace_of_radiance_animation.nim:101-214) at 64x48 / 4 spp, three frames: the .264 file
+    equals the oracle's pipeline byte for byte and the .mp4 decodes to the same luma."""
+    es, mp4 = str(tmp_path / "anim.264"), str(tmp_path / "anim.mp4")
+    n = tor.render_animation_mp4(tor.Animation(height=48, width=64), es, mp4, samples_per_pixel=4, max_frames=3,
+                                 ctx=gpu_ctx)
+    assert n == 3
+    want = oracle.h264_header(64, 48)
+    lumas = []
+    an = oracle.Animation(height=48, width=64)
+    for _ in range(3):
+        cam, world = an.next_frame(skip=6)
+        img = oracle.render(48, 64, 4, cam, world, math="libm")
+        y, cb, cr = oracle.rgb_to_ycbcr420(oracle.to_rgb_raw(img))
+        want += oracle.h264_frame(y, cb, cr)
+        lumas.append(y)
+    assert open(es, "rb").read() == want
+    cv2 = pytest.importorskip("cv2")
+    cap = cv2.VideoCapture(mp4)
+    assert cap.isOpened() and int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 3
+    cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+    for k in range(3):
+        ok, fr = cap.read()
+        assert ok and np.array_equal(fr.reshape(48, 64), lumas[k])

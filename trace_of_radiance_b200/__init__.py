@@ -9,6 +9,9 @@ sm_100a library and a CUDA device.
 from .api import (  # noqa: F401
     Animation,
     PinnedBuffer,
+    H264Encoder,
+    MP4Muxer,
+    render_animation_mp4,
     render_animation,
     HITTABLE_DTYPE,
     Camera,

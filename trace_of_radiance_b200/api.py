@@ -48,6 +48,7 @@ def TOR_FAST_SUBSTREAMS(n):
 
 TOR_FLAG_COUNT_SEGMENTS = 0x100
 TOR_FLAG_ROW_MAJOR_QUEUE = 0x400  # BVH route without the longest-pixel-first pre-pass (same image)
+TOR_FLAG_RGB_ROWS_AS_WRITTEN = 0x800  # video export: keep io/rgb.nim:29-31's off-by-one row indexing
 TOR_FLAG_BRUTE_FORCE = 0x200  # scan every object like hittables_lists.nim:48-55 instead of the BVH (same image)
 
 EXPORTED_SYMBOLS = [
@@ -55,7 +56,8 @@ EXPORTED_SYMBOLS = [
     "tor_scene_upload", "tor_render_device_async", "tor_sync", "tor_get_counters", "tor_last_kernel_ms",
     "tor_launch_count", "tor_measure_fp64_peak", "tor_get_traversal_counters", "tor_scene_info", "tor_camera_make", "tor_random_scene", "tor_export_ppm", "tor_quantise_rgb8", "tor_animation_create",
     "tor_animation_next_frame", "tor_animation_destroy", "tor_render_rgb8", "tor_render_rgb8_async", "tor_host_alloc",
-    "tor_host_free",
+    "tor_host_free", "tor_render_ycbcr420", "tor_render_ycbcr420_async", "tor_h264_open", "tor_h264_frame_buffer",
+    "tor_h264_flush_frame", "tor_h264_finish", "tor_mp4_mux_h264_file",
 ]
 
 
@@ -106,6 +108,13 @@ def load_library():
     L.tor_render_rgb8.argtypes = [vp, C.POINTER(_CCanvas), C.POINTER(_CCamera), vp, C.c_int64, C.c_int64, C.c_int64,
                                   C.c_uint32, vp]
     L.tor_render_rgb8_async.argtypes = L.tor_render_rgb8.argtypes
+    L.tor_render_ycbcr420.argtypes = L.tor_render_rgb8.argtypes
+    L.tor_render_ycbcr420_async.argtypes = L.tor_render_rgb8.argtypes
+    L.tor_h264_open.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.tor_h264_frame_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64)]
+    L.tor_h264_flush_frame.argtypes = [vp]
+    L.tor_h264_finish.argtypes = [vp]
+    L.tor_mp4_mux_h264_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32]
     L.tor_host_alloc.argtypes = [C.c_size_t]
     L.tor_host_alloc.restype = vp
     L.tor_host_free.argtypes = [vp]
@@ -365,6 +374,19 @@ class Context:
                        flags, out.ctypes.data))
         return out
 
+    def render_ycbcr420(self, canvas, cam, world, max_depth, flags=0, out=None, wait=True):
+        """render + io/rgb.nim quantisation + io/color_conversions.nim BT.601 4:2:0 conversion on the device.  `out`:
+        uint8 array of nrows*ncols*3/2 bytes (Y' plane, Cb, Cr), e.g. H264Encoder.frame; returns (Y, Cb, Cr) views."""
+        h, w = canvas.nrows, canvas.ncols
+        if out is None:
+            out = np.empty(h * w * 3 // 2, dtype=np.uint8)
+        c = _CCanvas(None, h, w, canvas.samples_per_pixel, canvas.gamma_correction)
+        objs = world.objects
+        fn = self.L.tor_render_ycbcr420 if wait else self.L.tor_render_ycbcr420_async
+        self._check(fn(self.h, C.byref(c), C.byref(cam.c), objs.ctypes.data, len(objs), objs.dtype.itemsize, max_depth,
+                       flags, out.ctypes.data))
+        return split_ycbcr420(out, h, w)
+
     def render_raw(self, canvas, cam, objects_ptr, length, stride, max_depth, flags=0):
         """Same call with an explicit (pointer, len, stride) — e.g. the 120-byte Nim variant encoding."""
         c = canvas._c()
@@ -434,6 +456,109 @@ class PinnedBuffer:
                 self.ptr = None
         except Exception:
             pass
+
+
+def split_ycbcr420(buf, height, width):
+    """Views of a contiguous Y'CbCr 4:2:0 frame buffer: Y (h, w), Cb and Cr (h/2, w/2)."""
+    n, q = height * width, (height // 2) * (width // 2)
+    flat = buf.reshape(-1)
+    return (flat[:n].reshape(height, width), flat[n:n + q].reshape(height // 2, width // 2),
+            flat[n + q:n + 2 * q].reshape(height // 2, width // 2))
+
+
+class H264Encoder:
+    """io/h264.nim `H264Encoder`: Baseline SPS/PPS + one I_PCM slice per frame, written to `path`.
+
+        enc = H264Encoder.init(width, height, path); Y, Cb, Cr = enc.getFrameBuffers(); ...; enc.flushFrame(); enc.finish()
+    """
+
+    def __init__(self):
+        self.L = load_library()
+        self.h = None
+
+    @classmethod
+    def init(cls, width, height, path):
+        """h264.nim:159-168 (takes a path instead of a Nim File)."""
+        self = cls()
+        h = C.c_void_p()
+        rc = self.L.tor_h264_open(os.fsencode(path), width, height, C.byref(h))
+        if rc:
+            raise TorError(rc, f"tor_h264_open({path}, {width}x{height}): dimensions must be multiples of 16")
+        self.h, self.width, self.height = h, width, height
+        p, n = C.c_void_p(), C.c_int64()
+        self.L.tor_h264_frame_buffer(self.h, C.byref(p), C.byref(n))
+        self.frame = np.ctypeslib.as_array((C.c_uint8 * n.value).from_address(p.value))
+        return self
+
+    def getFrameBuffers(self):
+        """h264.nim:207-224"""
+        return split_ycbcr420(self.frame, self.height, self.width)
+
+    def getFrameBuffer(self):
+        """h264.nim:226-236"""
+        return self.frame
+
+    def flushFrame(self):
+        """h264.nim:249-259"""
+        rc = self.L.tor_h264_flush_frame(self.h)
+        if rc:
+            raise TorError(rc, "tor_h264_flush_frame")
+
+    def finish(self):
+        """h264.nim:170-173 (also closes the file)."""
+        if self.h is not None:
+            self.frame = None
+            rc = self.L.tor_h264_finish(self.h)
+            self.h = None
+            if rc:
+                raise TorError(rc, "tor_h264_finish")
+
+
+class MP4Muxer:
+    """io/mp4.nim `MP4Muxer` (:104-163)."""
+
+    def initialize(self, path, width, height):
+        self.path, self.width, self.height = path, int(width), int(height)
+        return self
+
+    def writeMP4_from(self, src, fps=30):
+        rc = load_library().tor_mp4_mux_h264_file(os.fsencode(src), os.fsencode(self.path), self.width, self.height, fps)
+        if rc:
+            raise TorError(rc, f"tor_mp4_mux_h264_file({src} -> {self.path})")
+
+    def close(self):
+        pass
+
+
+def render_animation_mp4(animation, dest_264, dest_mp4, samples_per_pixel=10, max_depth=50, gamma_correction=2.2, skip=6,
+                         max_frames=None, flags=0, ctx=None, fps=30):
+    """`main_animation_mp4` of trace_of_radiance_animation.nim:101-214: for every (camera, scene) of the animation
+    render, convert to Y'CbCr 4:2:0 (both on the device, straight into the encoder's page-locked frame buffer), flush
+    one I_PCM frame; then mux the .264 into an .mp4.  Returns the number of frames."""
+    h, w = animation_dims(animation)
+    canvas = Canvas.__new__(Canvas)
+    canvas.nrows, canvas.ncols, canvas.samples_per_pixel = h, w, int(samples_per_pixel)
+    canvas.gamma_correction = float(np.float32(gamma_correction))
+    canvas.pixels = None
+    own = ctx is None
+    ctx = ctx or Context()
+    enc = H264Encoder.init(w, h, dest_264)
+    n = 0
+    try:
+        for i, (cam, world) in enumerate(animation.scenes(skip=skip)):
+            if max_frames is not None and i >= max_frames:
+                break
+            ctx.render_ycbcr420(canvas, cam, world, max_depth, flags=flags, out=enc.getFrameBuffer())
+            enc.flushFrame()
+            n += 1
+    finally:
+        enc.finish()
+        if own:
+            ctx.close()
+    mux = MP4Muxer().initialize(dest_mp4, w, h)
+    mux.writeMP4_from(dest_264, fps=fps)
+    mux.close()
+    return n
 
 
 def render_animation(animation, samples_per_pixel=100, max_depth=50, gamma_correction=2.2, skip=6, in_flight=4,

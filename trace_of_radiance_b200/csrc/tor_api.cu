@@ -631,6 +631,52 @@ int tor_render_rgb8_async(tor_ctx* ctx, const tor_canvas* canvas, const tor_came
   return TOR_OK;
 }
 
+int tor_render_ycbcr420_async(tor_ctx* ctx, const tor_canvas* canvas, const tor_camera* cam, const void* objects,
+                              int64_t len, int64_t stride, int64_t max_depth, uint32_t flags, uint8_t* ycbcr_out) {
+  if (!ctx) return TOR_ERR_INVALID_ARG;
+  if (!canvas || !ycbcr_out) return fail(ctx, TOR_ERR_INVALID_ARG, "canvas or ycbcr_out is NULL");
+  const int32_t nrows = canvas->nrows, ncols = canvas->ncols;
+  int rc = check_canvas_dims(ctx, nrows, ncols, canvas->samples_per_pixel, max_depth, 0, nrows, 1);
+  if (rc) return rc;
+  if ((nrows & 1) || (ncols & 1))  // color_conversions.nim:201-202
+    return fail(ctx, TOR_ERR_INVALID_ARG, "Y'CbCr 4:2:0 needs an even width and height");
+  rc = set_scene(ctx, cam, objects, len, stride);
+  if (rc) return rc;
+  DeviceState& d = ctx->devs[0];
+  const size_t npix = (size_t)nrows * ncols;
+  const size_t nbytes = npix + 2 * (npix / 4);
+  rc = ensure_capacity(ctx, d, device_blob_bytes(ctx), npix * 3 * sizeof(double));
+  if (rc) return rc;
+  if (npix * 3 > d.rgb8_cap) {  // the same scratch buffer as the RGB8 output (3 bytes per pixel >= 1.5)
+    if (d.d_rgb8) cudaFree(d.d_rgb8);
+    d.d_rgb8 = nullptr;
+    d.rgb8_cap = 0;
+    TOR_CUDA(ctx, cudaMalloc(&d.d_rgb8, npix * 3));
+    d.rgb8_cap = npix * 3;
+  }
+  rc = upload_scene_to(ctx, d);
+  if (rc) return rc;
+  rc = launch_rows(ctx, d, d.d_pixels, nrows, ncols, canvas->samples_per_pixel, canvas->gamma_correction, max_depth,
+                   flags & ~TOR_FLAG_RGB_ROWS_AS_WRITTEN, 0, nrows, 1, d.stream, /*timed=*/true);
+  if (rc) return rc;
+  uint8_t* dY = d.d_rgb8;
+  uint8_t* dCb = dY + npix;
+  uint8_t* dCr = dCb + npix / 4;
+  tor::ycbcr420_kernel<<<(unsigned)((npix / 4 + 255) / 256), 256, 0, d.stream>>>(
+      d.d_pixels, nrows, ncols, (flags & TOR_FLAG_RGB_ROWS_AS_WRITTEN) ? 1 : 0, dY, dCb, dCr);
+  TOR_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  TOR_CUDA(ctx, cudaMemcpyAsync(ycbcr_out, d.d_rgb8, nbytes, cudaMemcpyDeviceToHost, d.stream));
+  return TOR_OK;
+}
+
+int tor_render_ycbcr420(tor_ctx* ctx, const tor_canvas* canvas, const tor_camera* cam, const void* objects, int64_t len,
+                        int64_t stride, int64_t max_depth, uint32_t flags, uint8_t* ycbcr_out) {
+  int rc = tor_render_ycbcr420_async(ctx, canvas, cam, objects, len, stride, max_depth, flags, ycbcr_out);
+  if (rc) return rc;
+  return tor_sync(ctx);
+}
+
 int tor_render_rgb8(tor_ctx* ctx, const tor_canvas* canvas, const tor_camera* cam, const void* objects, int64_t len,
                     int64_t stride, int64_t max_depth, uint32_t flags, uint8_t* rgb8_out) {
   int rc = tor_render_rgb8_async(ctx, canvas, cam, objects, len, stride, max_depth, flags, rgb8_out);

@@ -578,4 +578,51 @@ __global__ void __launch_bounds__(256) quantise_rgb8_kernel(const double* __rest
   }
 }
 
+// io/rgb.nim:17-31 `toRGB_Raw` + io/color_conversions.nim:180-252 `rgbRaw_to_ycbcr420` (BT.601, video range, 4:2:0)
+// fused over the drawn canvas: one thread per 2x2 block quantises its four pixels (uint8(256 * clamp(c, 0, 0.999))),
+// forms the reference's 8-bit fixed-point luma per pixel and the chroma of the block from the four (B - Y'), (R - Y')
+// differences.  All integer arithmetic below stays inside the reference's uint16 / int16 ranges (|sums| <= 4 * 255,
+// products <= 255 * 160 in magnitude only where the reference's int16 does not overflow either: |R - Y'| <= 179), so
+// plain int gives the same bits.  `>>` on negative values is an arithmetic shift in CUDA as in Nim.
+// Output planes are top row first.  as_written != 0 reproduces rgb.nim:29-31 literally: output row i shows canvas row
+// nrows - i (one row off; output row 0, which the reference reads past the end of the buffer, is defined as 0).
+// Coefficients: color_conversions.nim:104-114,178 evaluated for BT.601: kr 77, kg 150, kb 29, fb 127, fr 160,
+// y_scale 110 (7 bits), y_min 16.
+__device__ __forceinline__ int rgb_level(double c) {  // rgb.nim:20-21 (NaN -> 0)
+  const double cl = c < 0.0 ? 0.0 : (c > 0.999 ? 0.999 : c);
+  return c != c ? 0 : (int)(256 * cl);
+}
+
+__global__ void __launch_bounds__(256) ycbcr420_kernel(const double* __restrict__ pixels, int32_t nrows, int32_t ncols,
+                                                       int32_t as_written, uint8_t* __restrict__ Y,
+                                                       uint8_t* __restrict__ Cb, uint8_t* __restrict__ Cr) {
+  const int32_t bw = ncols >> 1, bh = nrows >> 1;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)bw * bh) return;
+  const int32_t by = (int32_t)(t / bw), bx = (int32_t)(t - (long long)by * bw);
+  int tU = 0, tV = 0;
+#pragma unroll
+  for (int di = 0; di < 2; ++di) {
+    const int32_t i = 2 * by + di;  // output row, top first
+    const int32_t src = as_written ? nrows - i : nrows - 1 - i;
+#pragma unroll
+    for (int dj = 0; dj < 2; ++dj) {
+      const int32_t j = 2 * bx + dj;
+      int r = 0, g = 0, b = 0;
+      if (src < nrows) {
+        const double* p = pixels + 3ll * ((long long)src * ncols + j);
+        r = rgb_level(p[0]);
+        g = rgb_level(p[1]);
+        b = rgb_level(p[2]);
+      }
+      const int tY = (77 * r + 150 * g + 29 * b) >> 8;
+      tU += b - tY;
+      tV += r - tY;
+      Y[(long long)i * ncols + j] = (uint8_t)(((tY * 110) >> 7) + 16);
+    }
+  }
+  Cb[(long long)by * bw + bx] = (uint8_t)((((tU >> 2) * 127) >> 8) + 128);
+  Cr[(long long)by * bw + bx] = (uint8_t)((((tV >> 2) * 160) >> 8) + 128);
+}
+
 }  // namespace tor
