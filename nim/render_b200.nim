@@ -23,6 +23,9 @@ type
 const
   TOR_STRIDE_FLAT = 112
   TOR_MODE_EXACT = 0'u32
+  TOR_MODE_FAST = 1'u32      # split-stream mode (include/tor_b200.h): deterministic, float64, NOT the reference's image
+  # nim c -d:torSplitStream ... selects the split-stream mode for every render() call of the program
+  torFlags = when defined(torSplitStream): TOR_MODE_FAST else: TOR_MODE_EXACT
 
 {.push importc, cdecl, dynlib: "libtor_b200.so".}
 proc tor_ctx_create(devices: ptr cint, ndev: cint, ctx: ptr TorCtx): cint
@@ -30,6 +33,8 @@ proc tor_ctx_destroy(ctx: TorCtx)
 proc tor_last_error(ctx: TorCtx): cstring
 proc tor_render(ctx: TorCtx, canvas: ptr Canvas, cam: ptr Camera, objects: pointer,
                 len, stride, max_depth: int64, flags: uint32): cint
+proc tor_render_ycbcr420(ctx: TorCtx, canvas: ptr Canvas, cam: ptr Camera, objects: pointer,
+                         len, stride, max_depth: int64, flags: uint32, ycbcr_out: ptr UncheckedArray[uint8]): cint
 {.pop.}
 
 static:
@@ -51,14 +56,9 @@ func toFlat(mat: Material, h: var TorHittable) =
   of kDielectric:
     h.fuzz_or_ior = mat.fDielectric.refraction_index
 
-proc render*(canvas: var Canvas, cam: Camera, world: HittableList, max_depth: int) =
-  ## Same signature as trace_of_radiance/render.nim:49.  Synchronous: the image is complete on
-  ## return (the reference completes at syncRoot/exit(Weave)); Weave does not need to be initialised.
+proc toFlatList(world: HittableList): seq[TorHittable] =
   privateAccess(HittableList)   # len, objects        (hittables_lists.nim:20-24)
   privateAccess(MovingSphere)   # center0, time0, time1 (moving_spheres.nim:15-20)
-  if pointer(ctx).isNil:
-    doAssert tor_ctx_create(nil, 0, addr ctx) == 0, $tor_last_error(TorCtx(nil))
-
   var flat = newSeq[TorHittable](world.len)
   for i in 0 ..< world.len:
     let o = world.objects[i]
@@ -78,9 +78,33 @@ proc render*(canvas: var Canvas, cam: Camera, world: HittableList, max_depth: in
       flat[i].radius = s.radius
       s.material.toFlat(flat[i])
 
+  flat
+
+proc render*(canvas: var Canvas, cam: Camera, world: HittableList, max_depth: int) =
+  ## Same signature as trace_of_radiance/render.nim:49.  Synchronous: the image is complete on
+  ## return (the reference completes at syncRoot/exit(Weave)); Weave does not need to be initialised.
+  if pointer(ctx).isNil:
+    doAssert tor_ctx_create(nil, 0, addr ctx) == 0, $tor_last_error(TorCtx(nil))
+  var flat = world.toFlatList()
   var camCopy = cam
-  let rc = tor_render(ctx, addr canvas, addr camCopy, addr flat[0], int64 world.len,
-                      TOR_STRIDE_FLAT, int64 max_depth, TOR_MODE_EXACT)
+  let rc = tor_render(ctx, addr canvas, addr camCopy, addr flat[0], int64 flat.len,
+                      TOR_STRIDE_FLAT, int64 max_depth, torFlags)
+  doAssert rc == 0, $tor_last_error(ctx)
+
+proc renderYCbCr420*(canvas: var Canvas, cam: Camera, world: HittableList, max_depth: int,
+                     frame: ptr UncheckedArray[uint8]) =
+  ## For trace_of_radiance_animation.nim:181-195: replaces
+  ##   canvas.render(...); syncRoot(Weave); let rgb = canvas.toRGB_Raw(); rgbRaw_to_ycbcr420(...)
+  ## by one call that renders and converts on the device and writes Y', Cb, Cr straight into the encoder's frame
+  ## buffer (`encoder.getFrameBuffer()`, io/h264.nim:226-236); `encoder.flushFrame()` follows as before.
+  ## canvas.pixels is not written.  Rows come out top first (io/rgb.nim:29-31 is one row off; pass
+  ## TOR_FLAG_RGB_ROWS_AS_WRITTEN = 0x800 in the flags to keep that).
+  if pointer(ctx).isNil:
+    doAssert tor_ctx_create(nil, 0, addr ctx) == 0, $tor_last_error(TorCtx(nil))
+  var flat = world.toFlatList()
+  var camCopy = cam
+  let rc = tor_render_ycbcr420(ctx, addr canvas, addr camCopy, addr flat[0], int64 flat.len,
+                               TOR_STRIDE_FLAT, int64 max_depth, torFlags, frame)
   doAssert rc == 0, $tor_last_error(ctx)
 
   # Alternative without the per-object copy: pass the raw variant array,
