@@ -18,8 +18,15 @@ big = T.random_scene(0xFACADE, 50).list()
 cv = T.newCanvas(12, 20, 4, 2.2)
 ctx.render(cv, cam, big, 50)
 print("rgb8", ctx.render_rgb8(cv, cam, world, 50).sum())
+for n in (1, 4, 32):  # split-stream mode: (pixel, range) units + substream_reduce_kernel
+    cv = T.newCanvas(24, 40, 10, 2.2)
+    ctx.render(cv, cam, world, 50, flags=T.api.TOR_MODE_FAST | T.api.TOR_FAST_SUBSTREAMS(n))
+    print("split", n, float(cv.pixels.sum()))
+cv = T.newCanvas(24, 40, 4, 2.2)
+y, cb, cr = ctx.render_ycbcr420(cv, cam, world, 50, flags=T.api.TOR_MODE_FAST)  # ycbcr420_kernel
+print("ycbcr", int(y.sum()), int(cb.sum()), int(cr.sum()))
 PY
 compute-sanitizer --tool memcheck --error-exitcode 3 python /tmp/san.py > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"
-tail -6 gpurun_out/sanitizer_memcheck.log
+tail -9 gpurun_out/sanitizer_memcheck.log
 compute-sanitizer --tool racecheck --error-exitcode 3 python /tmp/san.py > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"
 tail -4 gpurun_out/sanitizer_racecheck.log

@@ -108,29 +108,23 @@ LaunchPlan plan_for(const tor::SceneView& sv, int max_smem_optin) {
 
 // The hierarchy is staged in shared memory only while two CTAs still fit on an SM (the traversal is
 // latency-bound and wants the warps); beyond that the nodes, then nothing, and L1/L2 serve the rest.
-template <int B>
+template <int B, bool CHUNKED>
 BvhLaunchPlan bvh_plan_b(const tor::BvhView& bv, size_t budget) {
-  if (bv.total_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<B, 2>, 2, bv.total_bytes, B};
-  if (bv.nodes_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<B, 1>, 1, bv.nodes_bytes, B};
-  return BvhLaunchPlan{tor::render_bvh_kernel<B, 0>, 0, 0, B};
+  if (bv.total_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<B, 2, CHUNKED>, 2, bv.total_bytes, B};
+  if (bv.nodes_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<B, 1, CHUNKED>, 1, bv.nodes_bytes, B};
+  return BvhLaunchPlan{tor::render_bvh_kernel<B, 0, CHUNKED>, 0, 0, B};
 }
 
-BvhLaunchPlan bvh_plan_for(const tor::BvhView& bv, int max_smem_per_sm, int max_smem_optin) {
-  static const int block = [] {  // developer tuning knob: CTA size (registers per lane follow from it)
+// chunked: the warp-level queue of the split-stream mode (tor_kernels_bvh.cuh); otherwise one atomic per lane
+BvhLaunchPlan bvh_plan_for(const tor::BvhView& bv, int max_smem_per_sm, int max_smem_optin, bool chunked) {
+  static const int block = [] {  // developer tuning knob: CTA size 256 (two CTAs per SM) or 512 (one)
     const char* e = getenv("TOR_BVH_BLOCK");
     return e ? atoi(e) : kBlock;
   }();
   const size_t half = (size_t)max_smem_per_sm / 2 - 2048;
   const size_t whole = (size_t)max_smem_optin;
-  switch (block) {
-    case 288: return bvh_plan_b<288>(bv, half);
-    case 320: return bvh_plan_b<320>(bv, half);
-    case 384: return bvh_plan_b<384>(bv, half);
-    case 512: return bvh_plan_b<512>(bv, whole);
-    case 768: return bvh_plan_b<768>(bv, whole);
-    case 1024: return bvh_plan_b<1024>(bv, whole);
-    default: return bvh_plan_b<kBlock>(bv, half);
-  }
+  if (block == 512) return chunked ? bvh_plan_b<512, true>(bv, whole) : bvh_plan_b<512, false>(bv, whole);
+  return chunked ? bvh_plan_b<kBlock, true>(bv, half) : bvh_plan_b<kBlock, false>(bv, half);
 }
 
 // kRefill of the BVH kernel (tor_kernels_bvh.cuh).  The environment variable is a developer tuning knob;
@@ -333,9 +327,17 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     P.counters = d.d_counters;
     P.refill = bvh_refill();
     P.lanes_per_warp = 32;
+    {
+      static const int chunk_env = [] {  // developer tuning knob: queue slots per warp-level fetch (0 = default rule)
+        const char* e = getenv("TOR_BVH_CHUNK");
+        int c = e ? atoi(e) : 0;
+        return c <= 0 ? 0 : (c < 32 ? 32 : (c > 4096 ? 4096 : c / 32 * 32));
+      }();
+      P.chunk = (uint32_t)chunk_env;
+    }
     if (P.refill > P.lanes_per_warp) P.refill = P.lanes_per_warp;
 
-    BvhLaunchPlan plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin);
+    BvhLaunchPlan plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin, /*chunked=*/sub_log2 != 0);
     const int block = plan.block;
     TOR_CUDA(ctx, cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     int per_sm = 0;
@@ -351,6 +353,11 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     // pixel, only their segment counts kept) ranks the pixels; the most expensive ones are dealt to the lanes so that
     // every warp starts with the same mix of costs, the rest is queued most-expensive-first.
     const unsigned long long lanes = (unsigned long long)grid * block;
+    // Split-stream queue: a warp takes 64 consecutive units at a time when every lane gets plenty of them, 32 (one
+    // per lane) otherwise and over the last four units per lane, so that no warp ends the render on a long chunk of
+    // neighbouring — i.e. similarly expensive — units.
+    P.chunk_guard = lanes * 4ull;
+    if (P.chunk == 0) P.chunk = (total_px << sub_log2) >= lanes * 64ull ? 64u : 32u;
     // below 256 spp the pre-pass costs more than the order gains (C1: +1 ms); split-stream units are short and
     // plentiful, so they need no ranking either
     const int32_t pre = (spp >= 256 && sub_log2 == 0) ? 8 : 0;
@@ -413,9 +420,12 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       P.order = d.d_order;
       P.first_wave = first_wave;
       P.total_slots = (uint32_t)slots;
-    } else if (reorder && !getenv("TOR_BVH_NO_SCRAMBLE")) {
-      // no cost information (few samples per pixel): scatter the image over the warps so that expensive neighbours
-      // do not share one (BvhRenderParams::scramble)
+    } else if (reorder && sub_log2 == 0 && !getenv("TOR_BVH_NO_SCRAMBLE")) {
+      // exact mode without cost information (few samples per pixel): scatter the image over the warps so that
+      // expensive neighbours do not share one (BvhRenderParams::scramble).  Split-stream units are short, so there
+      // the queue stays in image order and the lanes of a warp work on neighbouring pixels.
+      P.scramble = coprime_near_golden((uint32_t)total_px);
+    } else if (sub_log2 && getenv("TOR_BVH_FAST_SCRAMBLE")) {  // developer knob: the scattered order in split-stream mode
       P.scramble = coprime_near_golden((uint32_t)total_px);
     }
     plan.fn<<<grid, block, plan.smem, stream>>>(P);

@@ -60,6 +60,10 @@ struct BvhRenderParams {
   // (3 doubles at 3*unit) and substream_reduce_kernel adds them up.  sub_log2 == 0 is the exact mode: the unit is
   // the pixel and its one stream is the reference's (render.nim:59-67).
   uint32_t sub_log2;
+  // Queue slots a warp takes at once when there is no cost-ranked order (multiple of 32), and the distance from the
+  // end of the queue below which warps take 32 at a time so that the render does not end on one warp's long chunk.
+  uint32_t chunk;
+  unsigned long long chunk_guard;
 };
 
 // One object of a leaf (or of the "always" list) against the ray: the reference's arithmetic
@@ -117,8 +121,8 @@ __device__ __forceinline__ V3 rec_center(const double2* __restrict__ r, uint32_t
   return c0;
 }
 
-template <int BLOCK, int STAGE>
-__global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 384 ? 2 : 1)) render_bvh_kernel(const __grid_constant__ BvhRenderParams P) {
+template <int BLOCK, int STAGE, bool CHUNKED>
+__global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_bvh_kernel(const __grid_constant__ BvhRenderParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t stage_bar;
 
@@ -145,6 +149,11 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
   const float4* __restrict__ nodes = reinterpret_cast<const float4*>((STAGE >= 1 ? smem : P.blob) + bv.off_nodes);
   const double2* __restrict__ recs = reinterpret_cast<const double2*>((STAGE == 2 ? smem : P.blob) + bv.off_objs);
   const uint32_t nodes_sa = smem_u32(smem) + bv.off_nodes;  // meaningful for STAGE >= 1 only
+
+  __shared__ unsigned long long warp_chunk[CHUNKED ? BLOCK / 32 : 1][2];  // [next, end) slots of each warp's chunk
+  unsigned long long* const wchunk = warp_chunk[CHUNKED ? tid >> 5 : 0];
+  if (CHUNKED && (tid & 31) == 0) wchunk[0] = wchunk[1] = 0ull;
+  __syncwarp();
 
   const double INF = __longlong_as_double(0x7ff0000000000000ll);
   const double t_min = 0.001;  // render.nim:28
@@ -223,6 +232,36 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
     }
   };
 
+  // queue slot -> work unit when there is no cost-ranked order: consecutive slots are the sample ranges of one pixel;
+  // the pixels come in row-major or scrambled order
+  auto unit_of_slot = [&](unsigned long long slot) -> uint32_t {
+    const unsigned long long ps = slot >> P.sub_log2;
+    const uint32_t px = P.scramble ? (uint32_t)((ps * (unsigned long long)P.scramble) % total_px) : (uint32_t)ps;
+    return (px << P.sub_log2) | ((uint32_t)slot & ((1u << P.sub_log2) - 1u));
+  };
+  // Starts work unit `pid`: samples [s_begin, s_end) of its pixel (the whole loop of render.nim:62 when
+  // sub_log2 == 0).  Returns false for an empty range, whose zero sum is written here.
+  auto begin_unit = [&]() -> bool {
+    pix_seg = 0;
+    const uint32_t px = pid >> P.sub_log2, sub = pid & ((1u << P.sub_log2) - 1u);
+    const int32_t s_begin = (int32_t)(((unsigned long long)sub * (unsigned long long)P.spp) >> P.sub_log2);
+    const int32_t s_end = (int32_t)(((unsigned long long)(sub + 1u) * (unsigned long long)P.spp) >> P.sub_log2);
+    if (s_end > s_begin) {
+      int32_t ri = (int32_t)(px / (uint32_t)P.ncols);
+      L.col = (int32_t)(px - (uint32_t)ri * (uint32_t)P.ncols);
+      L.row = P.row_begin + ri * P.row_step;
+      rng_seed_pixel(L.rng, L.row, L.col, sub);  // render.nim:59-60
+      L.pix = v3(0, 0, 0);
+      L.sample = P.spp - (s_end - s_begin);  // counts up to spp
+      active = true;
+      need_sample = true;
+      return true;
+    }
+    double* out = P.pixels + 3ull * pid;  // no samples: the zero colour goes through draw() (canvas.nim:49-54)
+    out[0] = out[1] = out[2] = 0.0;
+    return false;
+  };
+
   for (;;) {
     // =================================================================== phase S
     if (active && trav_done) {
@@ -269,50 +308,71 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : (BLOCK <= 
       }
     }
     __syncwarp();
-    if (need_pixel) {
-      need_pixel = false;
-      active = false;
-      for (;;) {
-        if (first_fetch) {  // dealt pixel of this lane, if any
-          first_fetch = false;
-          const uint32_t gid = blockIdx.x * BLOCK + tid;
-          pid = gid < P.first_wave ? P.order[gid] : 0xffffffffu;
-          if (pid == 0xffffffffu) continue;
-        } else if (P.first_wave) {
-          const unsigned long long slot = P.first_wave + atomicAdd(P.work_counter, 1ull);
-          if (slot >= P.total_slots) break;
-          pid = P.order[slot];
-        } else {
-          const unsigned long long slot = atomicAdd(P.work_counter, 1ull);
-          if (slot >= total_units) break;
-          if (P.order) {
+    // ---- new work units
+    if constexpr (!CHUNKED) {
+      // One atomic per lane.  Serves the exact mode: the cost-ranked queue (order != NULL: the lane's dealt pixel
+      // first, then the queue) and the row-major / scrambled pixel queue of renders without a cost pre-pass.
+      if (need_pixel) {
+        need_pixel = false;
+        active = false;
+        for (;;) {
+          if (first_fetch) {  // dealt pixel of this lane, if any
+            first_fetch = false;
+            const uint32_t gid = blockIdx.x * BLOCK + tid;
+            pid = gid < P.first_wave ? P.order[gid] : 0xffffffffu;
+            if (pid == 0xffffffffu) continue;
+          } else if (P.first_wave) {
+            const unsigned long long slot = P.first_wave + atomicAdd(P.work_counter, 1ull);
+            if (slot >= P.total_slots) break;
             pid = P.order[slot];
           } else {
-            // consecutive slots are the sample ranges of one pixel (lanes that fetch together trace similar rays);
-            // the pixels themselves come in row-major or scrambled order
-            const unsigned long long ps = slot >> P.sub_log2;
-            const uint32_t px = P.scramble ? (uint32_t)((ps * (unsigned long long)P.scramble) % total_px) : (uint32_t)ps;
-            pid = (px << P.sub_log2) | ((uint32_t)slot & ((1u << P.sub_log2) - 1u));
+            const unsigned long long slot = atomicAdd(P.work_counter, 1ull);
+            if (slot >= total_units) break;
+            pid = P.order ? P.order[slot] : unit_of_slot(slot);
+          }
+          if (begin_unit()) break;
+        }
+      }
+    } else {
+      // Split-stream mode: the WARP takes `chunk` consecutive queue slots at a time from the global counter and its
+      // lanes consume them in order (warp_chunk[] in shared memory).  Consecutive slots are the sample ranges of one
+      // pixel, then the next pixel of the row, so the lanes of a warp trace neighbouring rays: the same BVH subtrees,
+      // the same few materials.  Warp-uniform loop: each pass hands one slot to every lane that still needs one.
+      for (;;) {
+        const unsigned want = __ballot_sync(0xffffffffu, need_pixel);
+        if (!want) break;
+        const int lane = tid & 31, leader = __ffs(want) - 1;
+        unsigned long long base = 0;
+        int take = 0;
+        if (lane == leader) {
+          unsigned long long next = wchunk[0], end = wchunk[1];
+          if (next >= end) {  // chunk used up: take the next one (short chunks near the end of the queue)
+            const unsigned long long head = *(volatile unsigned long long*)P.work_counter;
+            const unsigned long long ch = head + P.chunk_guard < total_units ? (unsigned long long)P.chunk : 32ull;
+            next = atomicAdd(P.work_counter, ch);
+            end = next + ch < total_units ? next + ch : total_units;
+            if (next > end) next = end;
+          }
+          const unsigned long long avail = end - next;
+          const int n = __popc(want);
+          take = avail < (unsigned long long)n ? (int)avail : n;
+          base = next;
+          wchunk[0] = next + (unsigned long long)take;
+          wchunk[1] = end;
+        }
+        __syncwarp();  // the next pass may have another leader: order the shared-memory update
+        base = __shfl_sync(0xffffffffu, base, leader);
+        take = __shfl_sync(0xffffffffu, take, leader);
+        if (need_pixel) {
+          const int rank = __popc(want & ((1u << lane) - 1u));
+          if (take == 0) {  // a fresh chunk came back empty: the queue is exhausted
+            need_pixel = false;
+            active = false;
+          } else if (rank < take) {
+            pid = unit_of_slot(base + (unsigned long long)rank);
+            need_pixel = !begin_unit();  // an empty sample range (spp < ranges): take another slot in the next pass
           }
         }
-        pix_seg = 0;
-        const uint32_t px = pid >> P.sub_log2, sub = pid & ((1u << P.sub_log2) - 1u);
-        // samples [s_begin, s_end) of the pixel; the whole loop of render.nim:62 when sub_log2 == 0
-        const int32_t s_begin = (int32_t)(((unsigned long long)sub * (unsigned long long)P.spp) >> P.sub_log2);
-        const int32_t s_end = (int32_t)(((unsigned long long)(sub + 1u) * (unsigned long long)P.spp) >> P.sub_log2);
-        if (s_end > s_begin) {
-          int32_t ri = (int32_t)(px / (uint32_t)P.ncols);
-          L.col = (int32_t)(px - (uint32_t)ri * (uint32_t)P.ncols);
-          L.row = P.row_begin + ri * P.row_step;
-          rng_seed_pixel(L.rng, L.row, L.col, sub);  // render.nim:59-60
-          L.pix = v3(0, 0, 0);
-          L.sample = P.spp - (s_end - s_begin);  // counts up to spp
-          active = true;
-          need_sample = true;
-          break;
-        }
-        double* out = P.pixels + 3ull * pid;  // no samples: the zero colour goes through draw() (canvas.nim:49-54)
-        out[0] = out[1] = out[2] = 0.0;
       }
     }
     if (!__any_sync(0xffffffffu, active)) break;
