@@ -334,7 +334,24 @@ def _run_ours_on_stream(args, wl, rank, world_size, local_rank, dev, torch, dist
         if world_size > 1:
             dist.all_reduce(ft, op=dist.ReduceOp.MAX)
         fms = float(ft[0]) / args.steps
+        # the same through the host-buffer call
+        def fast_e2e_step():
+            if world_size == 1:
+                ctx.render(canvas, cam, scene, depth, flags=fl)
+            else:
+                R.render(canvas, cam, scene, depth, flags=fl)
+
+        fast_e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fast_e2e_step()
+        barrier()
+        tf = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
         split = {"value": rays_per_step / (fms * 1e-3) / 1e6, "unit": "Mray/s", "ms_per_step": fms,
+                 "e2e": rays_per_step * e2e_steps / float(tf[0]) / 1e6,
                  "flags": "TOR_MODE_FAST (automatic substream count: 2^24 / pixels, <= spp, <= 32)",
                  "parity": "bit-exact vs the oracle's render_split; vs the reference image: within 4*sqrt(2)*sigma/"
                            "sqrt(spp) per pixel (tests/test_split_stream.py)"}

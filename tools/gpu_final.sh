@@ -14,6 +14,10 @@ grep -c render_bvh gpurun_out/${TAG}_launches_bench_c2.csv
 ncu --set full --clock-control none --import-source on -k regex:render_bvh -s 1 -c 1 -f -o gpurun_out/${TAG}_prof_bvh \
     python tools/sweep.py --dims 450 800 128 2 --rowmajor > gpurun_out/${TAG}_ncu_bvh.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_bvh.log
+# the same capture for the split-stream (chunked queue) variant of the kernel
+ncu --set full --clock-control none --import-source on -k regex:render_bvh -s 1 -c 1 -f -o gpurun_out/${TAG}_prof_bvh_split \
+    python tools/sweep.py --dims 450 800 128 2 --fast > gpurun_out/${TAG}_ncu_bvh_split.log 2>&1
+tail -1 gpurun_out/${TAG}_ncu_bvh_split.log
 # DRAM traffic of one full C2 launch of the main render kernel (the second render_bvh launch; the first is the cost pre-pass)
 ncu --set full --clock-control none -k regex:render_bvh -s 1 -c 1 -f -o gpurun_out/${TAG}_prof_c2_main \
     python tools/sweep.py --dims 675 1200 500 1 > gpurun_out/${TAG}_ncu_c2.log 2>&1

@@ -339,6 +339,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
 
     BvhLaunchPlan plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin, /*chunked=*/sub_log2 != 0);
     const int block = plan.block;
+    BvhLaunchPlan main_plan = plan;  // the cost pre-pass always runs `plan`; the main launch may use the chunked queue
     TOR_CUDA(ctx, cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     int per_sm = 0;
     TOR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, block, plan.smem));
@@ -382,7 +383,11 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     if (P.refill > (P.lanes_per_warp * 5) / 8) P.refill = (P.lanes_per_warp * 5) / 8;
     if (P.refill < 1) P.refill = 1;
     if (reorder && pre > 0 && P.lanes_per_warp == 32 && (block % 32) == 0) {
-      const uint32_t warps = (uint32_t)(lanes / 32);
+      static const bool deal = [] {  // developer knob: TOR_BVH_EXACT_DEAL=0 queues every pixel (no dealt first wave)
+        const char* e = getenv("TOR_BVH_EXACT_DEAL");
+        return !(e && atoi(e) == 0);
+      }();
+      const uint32_t warps = deal ? (uint32_t)(lanes / 32) : 0u;
       const uint32_t first_wave = warps * 32u;
       const uint32_t n = (uint32_t)total_px;
       const uint32_t n_first = n < first_wave ? n : first_wave;
@@ -412,9 +417,28 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
         int g = e ? atoi(e) : 8;
         return (uint32_t)((g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) ? g : 8);
       }();
-      tor::cost_histogram_kernel<<<sort_grid, 256, 0, stream>>>(d.d_cost, n, d.d_hist);
+      // Queue order: most expensive class first.  Default: coarse classes with the image order kept inside a class
+      // and warps that take 32 consecutive queue entries at a time (the CHUNKED kernel), so that after the dealt
+      // first wave the lanes of a warp work on neighbouring pixels of the same kind.  TOR_BVH_EXACT_QUEUE=percost
+      // selects the earlier scheme (one class per cost value, arbitrary order inside, one atomic per lane).
+      static const bool coherent = [] {
+        const char* e = getenv("TOR_BVH_EXACT_QUEUE");
+        return !(e && strcmp(e, "percost") == 0);
+      }();
+      tor::cost_histogram_kernel<<<sort_grid, 256, 0, stream>>>(d.d_cost, n, d.d_hist, coherent ? 1u : 0u);
       tor::cost_offsets_kernel<<<1, tor::kCostBuckets, 0, stream>>>(d.d_hist);
-      tor::cost_scatter_kernel<<<sort_grid, 256, 0, stream>>>(d.d_cost, n, d.d_hist, d.d_order, warps, group, n_first);
+      if (coherent) {
+        tor::cost_scatter_ordered_kernel<<<8, 1024, 0, stream>>>(d.d_cost, n, d.d_hist, d.d_order, warps, group, n_first,
+                                                              1u);
+        main_plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin, /*chunked=*/true);
+        TOR_CUDA(ctx, cudaFuncSetAttribute(main_plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)main_plan.smem));
+        P.chunk = 32;
+        P.chunk_guard = 0;
+      } else {
+        tor::cost_scatter_kernel<<<sort_grid, 256, 0, stream>>>(d.d_cost, n, d.d_hist, d.d_order, warps, group,
+                                                                n_first);
+      }
       TOR_CUDA(ctx, cudaGetLastError());
       ctx->launches += 4;
       P.order = d.d_order;
@@ -428,7 +452,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     } else if (sub_log2 && getenv("TOR_BVH_FAST_SCRAMBLE")) {  // developer knob: the scattered order in split-stream mode
       P.scramble = coprime_near_golden((uint32_t)total_px);
     }
-    plan.fn<<<grid, block, plan.smem, stream>>>(P);
+    main_plan.fn<<<grid, block, main_plan.smem, stream>>>(P);
     TOR_CUDA(ctx, cudaGetLastError());
     const unsigned long long nch = total_px * 3ull;
     if (sub_log2) {  // per-range partial sums -> pixel sums, fixed pairwise order

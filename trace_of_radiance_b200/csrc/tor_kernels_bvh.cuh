@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   const double t_min = 0.001;  // render.nim:28
   const unsigned long long total_px = (unsigned long long)P.nsel_rows * (unsigned long long)P.ncols;
   const unsigned long long total_units = total_px << P.sub_log2;
+  // length of the shared queue: everything, or what the cost-ranked order leaves after the dealt first wave
+  const unsigned long long queue_len = P.order ? (unsigned long long)(P.total_slots - P.first_wave) : total_units;
   const int refill = P.refill;
 
   Lane L;
@@ -338,6 +340,12 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
       // lanes consume them in order (warp_chunk[] in shared memory).  Consecutive slots are the sample ranges of one
       // pixel, then the next pixel of the row, so the lanes of a warp trace neighbouring rays: the same BVH subtrees,
       // the same few materials.  Warp-uniform loop: each pass hands one slot to every lane that still needs one.
+      if (first_fetch) {  // cost-ranked order: the pixel dealt to this lane, if any
+        first_fetch = false;
+        const uint32_t gid = blockIdx.x * BLOCK + tid;
+        pid = need_pixel && gid < P.first_wave ? P.order[gid] : 0xffffffffu;
+        if (pid != 0xffffffffu) need_pixel = !begin_unit();
+      }
       for (;;) {
         const unsigned want = __ballot_sync(0xffffffffu, need_pixel);
         if (!want) break;
@@ -348,9 +356,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
           unsigned long long next = wchunk[0], end = wchunk[1];
           if (next >= end) {  // chunk used up: take the next one (short chunks near the end of the queue)
             const unsigned long long head = *(volatile unsigned long long*)P.work_counter;
-            const unsigned long long ch = head + P.chunk_guard < total_units ? (unsigned long long)P.chunk : 32ull;
+            const unsigned long long ch = head + P.chunk_guard < queue_len ? (unsigned long long)P.chunk : 32ull;
             next = atomicAdd(P.work_counter, ch);
-            end = next + ch < total_units ? next + ch : total_units;
+            end = next + ch < queue_len ? next + ch : queue_len;
             if (next > end) next = end;
           }
           const unsigned long long avail = end - next;
@@ -369,7 +377,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
             need_pixel = false;
             active = false;
           } else if (rank < take) {
-            pid = unit_of_slot(base + (unsigned long long)rank);
+            const unsigned long long slot = base + (unsigned long long)rank;
+            pid = P.order ? P.order[P.first_wave + slot] : unit_of_slot(slot);
             need_pixel = !begin_unit();  // an empty sample range (spp < ranges): take another slot in the next pass
           }
         }
@@ -533,14 +542,22 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
 // head of the queue, so they start first and cheap pixels fill the tail.  The order cannot change the image.
 static constexpr int kCostBuckets = 1024;
 
+// Cost (bounce segments of the pre-pass samples) -> queue class.  coarse == 0: one class per cost value.  coarse != 0:
+// classes of 4 below 64 and of 8 above, so that neighbouring pixels of the same kind (sky, ground, a diffuse sphere)
+// share a class although their 8-sample costs differ by Monte-Carlo noise; inside a class the ordered scatter keeps the
+// image order, which is what makes the lanes of a warp work on neighbouring pixels.
+__device__ __forceinline__ uint32_t cost_class(uint32_t c, uint32_t coarse) {
+  if (coarse) c = c < 64u ? c >> 2 : 16u + ((c - 64u) >> 3);
+  return c < (uint32_t)kCostBuckets ? c : (uint32_t)kCostBuckets - 1u;
+}
+
 __global__ void __launch_bounds__(256) cost_histogram_kernel(const uint32_t* __restrict__ cost, uint32_t n,
-                                                             uint32_t* __restrict__ hist) {
+                                                             uint32_t* __restrict__ hist, uint32_t coarse) {
   __shared__ uint32_t h[kCostBuckets];
   for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x) h[i] = 0;
   __syncthreads();
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    uint32_t c = cost[i];
-    atomicAdd(&h[c < kCostBuckets ? c : kCostBuckets - 1], 1u);
+    atomicAdd(&h[cost_class(cost[i], coarse)], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x)
@@ -609,6 +626,39 @@ __global__ void __launch_bounds__(256) substream_reduce_kernel(const double* __r
     v = (j & ofs) ? w + v : v + w;
   }
   if (pc < n_pc && j == 0) out[pc] = v;
+}
+
+// The same scatter keeping the image order inside a class (approximately: exactly inside a warp's 32 consecutive
+// pixels, and window by window of gridDim * blockDim pixels, because the few blocks of this launch walk the image in
+// step).  Lanes of a warp with the same class take consecutive ranks with one atomic (warp-aggregated).
+__global__ void __launch_bounds__(1024) cost_scatter_ordered_kernel(const uint32_t* __restrict__ cost, uint32_t n,
+                                                                    uint32_t* __restrict__ offsets,
+                                                                    uint32_t* __restrict__ order, uint32_t warps,
+                                                                    uint32_t group, uint32_t n_first, uint32_t coarse) {
+  const uint32_t first_wave = warps * 32u, tier = warps * group;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+    const uint32_t i = i0 + threadIdx.x;
+    const bool in = i < n;
+    const uint32_t cls = in ? cost_class(cost[i], coarse) : 0xffffffffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, cls);
+    const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+    uint32_t base = 0;
+    if (in && lane == leader) base = atomicAdd(&offsets[cls], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (in) {
+      const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+      uint32_t slot;
+      if (pos < n_first) {
+        const uint32_t t = pos / tier, q = pos - t * tier;
+        slot = (q % warps) * 32u + t * group + q / warps;
+      } else {
+        slot = first_wave + (pos - n_first);
+      }
+      order[slot] = i;
+    }
+    __syncthreads();  // keeps the block's warps within one window of the image
+  }
 }
 
 // canvas.nim:47-54 `draw` over the sums the render kernel left in the framebuffer: one thread per channel,
