@@ -46,10 +46,12 @@ def ncu_traffic(kernel):
     return None
 
 
-def ncu_pipe_summary():
+def ncu_pipe_summary(variant="bvh"):
     """FP64 pipe / issue / SIMD utilisation of the render kernel from the committed `ncu --set full` capture
-    (profiles/r01f_ncu_bvh_800x450x128.json: same scene and camera at 800x450 / 128 spp); None if absent."""
-    p = os.path.join(ROOT, "profiles", "r01f_ncu_bvh_800x450x128.json")
+    (profiles/r01k_ncu_<variant>_800x450x128.json: same scene and camera at 800x450 / 128 spp; variant "bvh" = exact
+    mode with the row-major queue, "bvh_split" = split-stream mode); None if absent."""
+    name = f"r01k_ncu_{variant}_800x450x128.json"
+    p = os.path.join(ROOT, "profiles", name)
     if not os.path.exists(p):
         return None
     d = json.load(open(p))[0]
@@ -60,7 +62,7 @@ def ncu_pipe_summary():
     return {"fp64_pipe_active_pct": v("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
             "issue_active_pct": v("smsp__issue_active.avg.pct_of_peak_sustained_active"),
             "active_lanes_per_instruction": v("smsp__thread_inst_executed_per_inst_executed.ratio"),
-            "source": "profiles/r01f_ncu_bvh_800x450x128.json (captured under ncu, not a timing)"}
+            "source": f"profiles/{name} (captured under ncu, not a timing)"}
 
 
 def peaks():
@@ -351,7 +353,7 @@ def _run_ours_on_stream(args, wl, rank, world_size, local_rank, dev, torch, dist
         if world_size > 1:
             dist.all_reduce(tf, op=dist.ReduceOp.MAX)
         split = {"value": rays_per_step / (fms * 1e-3) / 1e6, "unit": "Mray/s", "ms_per_step": fms,
-                 "e2e": rays_per_step * e2e_steps / float(tf[0]) / 1e6,
+                 "e2e": rays_per_step * e2e_steps / float(tf[0]) / 1e6, "ncu": ncu_pipe_summary("bvh_split"),
                  "flags": "TOR_MODE_FAST (automatic substream count: 2^24 / pixels, <= spp, <= 32)",
                  "parity": "bit-exact vs the oracle's render_split; vs the reference image: within 4*sqrt(2)*sigma/"
                            "sqrt(spp) per pixel (tests/test_split_stream.py)"}

@@ -138,6 +138,18 @@ def test_gpu_split_stream_edges(tor, oracle, gpu_ctx, depth, spp, nsub):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("h,w,spp,nsub", [(1, 1, 5, 2), (2, 3, 4, 4), (1, 40, 7, 8), (33, 1, 3, 32), (7, 9, 64, 1)])
+def test_gpu_split_stream_tiny_canvases(tor, oracle, gpu_ctx, h, w, spp, nsub):
+    """Fewer work units than one warp's chunk, 1-pixel-wide / 1-pixel-high canvases (u or v divide by zero as in
+    render.nim:64-65): the warp-level queue hands out partial chunks and runs dry mid-pass."""
+    world, cam = tor.random_scene().list(), _book_cam(tor)
+    ref = oracle.render_split(h, w, spp, cam.as_array(), world.objects, nsub)
+    cv = tor.newCanvas(h, w, spp, 2.2)
+    gpu_ctx.render(cv, cam, world, 50, flags=_fast(tor, nsub))
+    assert cv.pixels.tobytes() == ref.tobytes()
+
+
+@pytest.mark.gpu
 def test_gpu_split_stream_partitions_and_rgb8(tor, oracle, gpu_ctx):
     world, cam = tor.random_scene().list(), _book_cam(tor)
     h, w, spp, fl = 54, 96, 12, _fast(tor, 4)

@@ -13,7 +13,7 @@ for rep in sys.argv[1:]:
     rows = list(csv.reader(txt.splitlines()))
     hdr, units = rows[0], rows[1]
     for vals in rows[2:]:
-        name = vals[hdr.index("Kernel Name")].split("<")[0].split("(")[0].replace("tor::", "").strip()
+        name = vals[hdr.index("Kernel Name")].split("<")[0].split("(")[0].replace("tor::", "").replace("void ", "").strip()
         total = 0.0
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = hdr.index(k)
