@@ -226,28 +226,20 @@ struct Builder {
         box_grow(bb[b], p.b);
         ++cnt[b];
       }
-      // Empty bins add nothing to a sweep: the right-hand area is carried over, and a left-hand candidate after an
-      // empty bin is the partition of the candidate before it (same cost, so never strictly better).  Most calls
-      // have a handful of objects in 16 bins, which makes this the bulk of the build time.
       double right_area[kBins];
       int right_cnt[kBins];
       Box acc;
       box_reset(acc);
       int c = 0;
-      double area = 0.0;
       for (int b = kBins - 1; b > 0; --b) {
-        if (cnt[b]) {
-          box_grow(acc, bb[b]);
-          c += cnt[b];
-          area = box_area(acc);
-        }
-        right_area[b] = area;
+        box_grow(acc, bb[b]);
+        c += cnt[b];
+        right_area[b] = box_area(acc);
         right_cnt[b] = c;
       }
       box_reset(acc);
       c = 0;
       for (int b = 0; b < kBins - 1; ++b) {
-        if (!cnt[b]) continue;
         box_grow(acc, bb[b]);
         c += cnt[b];
         if (c == 0 || right_cnt[b + 1] == 0) continue;
