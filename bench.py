@@ -352,7 +352,18 @@ def _run_ours_on_stream(args, wl, rank, world_size, local_rank, dev, torch, dist
         tf = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world_size > 1:
             dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        # algorithmic HBM bytes of the split-stream step: the exact mode's + one 24-byte partial sum per (pixel, range)
+        # written by the render kernel and read by substream_reduce_kernel
+        px = nrows * ncols
+        nsub = 1
+        while nsub * 2 <= min(32, spp, max(1, (1 << 24) // px)):
+            nsub *= 2
+        split_bytes = alg_bytes + 2 * 24 * my_rows * ncols * nsub
         split = {"value": rays_per_step / (fms * 1e-3) / 1e6, "unit": "Mray/s", "ms_per_step": fms,
+                 "substreams_per_pixel": nsub,
+                 "roofline": {"bound": "hbm", "achieved": split_bytes / (fms * 1e-3) / 1e9, "peak": hbm_peak,
+                              "unit": "GB/s", "frac": split_bytes / (fms * 1e-3) / 1e9 / hbm_peak,
+                              "algorithmic_bytes_per_step": split_bytes},
                  "e2e": rays_per_step * e2e_steps / float(tf[0]) / 1e6, "ncu": ncu_pipe_summary("bvh_split"),
                  "flags": "TOR_MODE_FAST (automatic substream count: 2^24 / pixels, <= spp, <= 32)",
                  "parity": "bit-exact vs the oracle's render_split; vs the reference image: within 4*sqrt(2)*sigma/"
