@@ -381,6 +381,16 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       P.lanes_per_warp = v < 1 ? 1 : (v > 32 ? 32 : v);
     }
     if (P.refill > (P.lanes_per_warp * 5) / 8) P.refill = (P.lanes_per_warp * 5) / 8;
+    if (sub_log2) {
+      // split-stream mode: the lanes of a warp trace neighbouring rays and finish their traversals close together,
+      // so waiting for more of them before shading costs little and shades more lanes at once
+      static const int fast_refill = [] {  // developer tuning knob
+        const char* e = getenv("TOR_BVH_REFILL_FAST");
+        int r = e ? atoi(e) : 20;
+        return r < 1 ? 1 : (r > 32 ? 32 : r);
+      }();
+      P.refill = fast_refill < P.lanes_per_warp ? fast_refill : P.lanes_per_warp;
+    }
     if (P.refill < 1) P.refill = 1;
     if (reorder && pre > 0 && P.lanes_per_warp == 32 && (block % 32) == 0) {
       static const bool deal = [] {  // developer knob: TOR_BVH_EXACT_DEAL=0 queues every pixel (no dealt first wave)
