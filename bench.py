@@ -354,10 +354,7 @@ def _run_ours_on_stream(args, wl, rank, world_size, local_rank, dev, torch, dist
             dist.all_reduce(tf, op=dist.ReduceOp.MAX)
         # algorithmic HBM bytes of the split-stream step: the exact mode's + one 24-byte partial sum per (pixel, range)
         # written by the render kernel and read by substream_reduce_kernel
-        px = nrows * ncols
-        nsub = 1
-        while nsub * 2 <= min(32, spp, max(1, (1 << 24) // px)):
-            nsub *= 2
+        nsub = T.api.fast_substream_count(fl, nrows, ncols, spp)
         split_bytes = alg_bytes + 2 * 24 * my_rows * ncols * nsub
         split = {"value": rays_per_step / (fms * 1e-3) / 1e6, "unit": "Mray/s", "ms_per_step": fms,
                  "substreams_per_pixel": nsub,

@@ -99,6 +99,25 @@ def test_stated_tolerance_against_the_exact_render(oracle, nsub):
         assert abs(mean_f[..., ch].mean() / mean_e[..., ch].mean() - 1.0) <= 0.005
 
 
+def test_automatic_substream_count(tor):
+    """The count depends on the flags, the FULL canvas and spp only (never on a row selection or the device), so every
+    partition of a canvas renders the same image: min(32, spp, 2^24 / pixels) rounded down to a power of two."""
+    A = tor.api
+    n = A.fast_substream_count
+    assert n(0, 675, 1200, 500) == 1  # exact mode
+    assert n(A.TOR_MODE_FAST, 216, 384, 100) == 32  # C1
+    assert n(A.TOR_MODE_FAST, 675, 1200, 500) == 16  # C2 / C3
+    assert n(A.TOR_MODE_FAST, 144, 256, 100) == 32  # C4
+    assert n(A.TOR_MODE_FAST, 2160, 3840, 2000) == 2  # C5
+    assert n(A.TOR_MODE_FAST, 216, 384, 5) == 4 and n(A.TOR_MODE_FAST, 216, 384, 1) == 1 and n(A.TOR_MODE_FAST, 8, 8, 0) == 1
+    assert n(A.TOR_MODE_FAST, 8192, 8192, 64) == 1
+    assert n(A.TOR_MODE_FAST | A.TOR_FAST_SUBSTREAMS(8), 675, 1200, 500) == 8
+    for bad in (A.TOR_MODE_FAST | A.TOR_FAST_SUBSTREAMS(3), A.TOR_MODE_FAST | A.TOR_FAST_SUBSTREAMS(64),
+                A.TOR_FAST_SUBSTREAMS(4), A.TOR_MODE_FAST | A.TOR_FLAG_BRUTE_FORCE):
+        with pytest.raises(A.TorError):
+            n(bad, 10, 10, 10)
+
+
 # ---------------------------------------------------------------------------- GPU: the CUDA path against the oracle
 def _book_cam(tor, aspect=16.0 / 9.0, t0=0.0, t1=1.0):
     return tor.camera((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, aspect, 0.1, 10.0, t0, t1)

@@ -57,7 +57,7 @@ EXPORTED_SYMBOLS = [
     "tor_launch_count", "tor_measure_fp64_peak", "tor_get_traversal_counters", "tor_scene_info", "tor_camera_make", "tor_random_scene", "tor_export_ppm", "tor_quantise_rgb8", "tor_animation_create",
     "tor_animation_next_frame", "tor_animation_destroy", "tor_render_rgb8", "tor_render_rgb8_async", "tor_host_alloc",
     "tor_host_free", "tor_render_ycbcr420", "tor_render_ycbcr420_async", "tor_h264_open", "tor_h264_frame_buffer",
-    "tor_h264_flush_frame", "tor_h264_finish", "tor_mp4_mux_h264_file",
+    "tor_h264_flush_frame", "tor_h264_finish", "tor_mp4_mux_h264_file", "tor_fast_substream_count",
 ]
 
 
@@ -115,6 +115,8 @@ def load_library():
     L.tor_h264_flush_frame.argtypes = [vp]
     L.tor_h264_finish.argtypes = [vp]
     L.tor_mp4_mux_h264_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32]
+    L.tor_fast_substream_count.argtypes = [C.c_uint32, C.c_int32, C.c_int32, C.c_int32]
+    L.tor_fast_substream_count.restype = C.c_int
     L.tor_host_alloc.argtypes = [C.c_size_t]
     L.tor_host_alloc.restype = vp
     L.tor_host_free.argtypes = [vp]
@@ -456,6 +458,14 @@ class PinnedBuffer:
                 self.ptr = None
         except Exception:
             pass
+
+
+def fast_substream_count(flags, height, width, samples_per_pixel):
+    """Sample ranges per pixel that a render with these flags would use (1 in exact mode); needs no device."""
+    n = load_library().tor_fast_substream_count(flags, height, width, samples_per_pixel)
+    if n < 0:
+        raise TorError(n, "invalid split-stream flags")
+    return n
 
 
 def split_ycbcr420(buf, height, width):

@@ -567,6 +567,13 @@ void tor_ctx_destroy(tor_ctx* ctx) {
   delete ctx;
 }
 
+int tor_fast_substream_count(uint32_t flags, int32_t nrows, int32_t ncols, int32_t samples_per_pixel) {
+  if (nrows <= 0 || ncols <= 0 || samples_per_pixel < 0) return TOR_ERR_INVALID_ARG;
+  uint32_t lg = 0;
+  int rc = substream_log2(nullptr, flags, nrows, ncols, samples_per_pixel, &lg);
+  return rc ? rc : (int)(1u << lg);
+}
+
 int tor_scene_upload(tor_ctx* ctx, const tor_camera* cam, const void* objects, int64_t len, int64_t stride) {
   if (!ctx) return TOR_ERR_INVALID_ARG;
   int rc = set_scene(ctx, cam, objects, len, stride);
