@@ -193,7 +193,7 @@ def run_reference(args, wl, rank):
         "e2e": {"value": value, "unit": "Mray/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------- our arm
@@ -405,10 +405,24 @@ def _run_ours_on_stream(args, wl, rank, world_size, local_rank, dev, torch, dist
             line["split_stream_mode"] = split
         if base:
             line["cpu_baseline"] = base
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
+
+
+RESULT_OUT = sys.stdout
+
+
+def keep_stdout_for_the_result_line():
+    """stdout must carry exactly one JSON line.  Libraries write to file descriptor 1 as well (NCCL prints its version
+    banner there when the first communicator is created), so fd 1 is pointed at stderr for the rest of the process and
+    the result line goes to a private copy of the original stdout."""
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
 
 def main():
+    keep_stdout_for_the_result_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
