@@ -5,6 +5,7 @@ container (needs /root/reference); the outputs are committed so nothing reads /r
                                (the reference's own render of random_scene, 384x216) — decoded, not re-rendered.
   c1_oracle_digest.json      : sha256 of the oracle's float64 framebuffer for config C1 in both math modes,
                                plus its deterministic counters (primary rays / segments).
+  book1_animation_gif_frames.npz : frames 0, 1, 50, 199 of /root/reference/media/book1_animation.gif, decoded.
   c1_split32_digest.json     : the same for the split-stream mode (32 substreams per pixel) and its PSNR against the PNG.
 """
 import hashlib
@@ -43,6 +44,18 @@ def main():
     with open(os.path.join(GOLD, "c1_oracle_digest.json"), "w") as f:
         json.dump(digest, f, indent=1)
     print(json.dumps(digest, indent=1))
+
+    # the reference's own animation (media/book1_animation.gif: 256x144, 200 frames = t_max 6.0, 30 ms per frame):
+    # four decoded frames, the weak golden (palette-quantised) that pins scenes_animated.nim — scene, physics steps and
+    # camera orbit — in tests/test_oracle_pins.py
+    gif = Image.open("/root/reference/media/book1_animation.gif")
+    assert gif.size == (256, 144) and gif.n_frames == 200
+    idx = [0, 1, 50, 199]
+    frames = []
+    for k in idx:
+        gif.seek(k)
+        frames.append(np.asarray(gif.convert("RGB")).copy())
+    np.savez_compressed(os.path.join(GOLD, "book1_animation_gif_frames.npz"), index=np.array(idx), rgb8=np.stack(frames))
 
     # split-stream mode (TOR_MODE_FAST) at C1 with 32 sample ranges per pixel: digest of the oracle's restatement and
     # its distance to the reference's PNG (an independent 100-spp estimate of the same image)
