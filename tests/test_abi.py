@@ -108,3 +108,40 @@ def test_animation_helper_equals_oracle(tor, oracle):  # scenes_animated.nim:90-
     # the frame count of the full C4 animation (t_max = 9.0) comes from float32 accumulation: 300
     n = sum(1 for _ in tor.Animation(height=8, width=8, t_max=9.0).scenes(skip=6))
     assert n == 300
+
+
+def test_header_is_plain_c_and_links_from_c(tor, tmp_path):
+    """The boundary is a C ABI: include/tor_b200.h must compile as C99 and a C program (what Nim's importc emits)
+    must link against libtor_b200.so.  Without a device the program sees TOR_ERR_NO_DEVICE from tor_ctx_create and
+    the device-free helpers still work; with one it creates and destroys a context."""
+    import shutil
+    import subprocess
+
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if not cc:
+        pytest.skip("no C compiler")
+    src = tmp_path / "consumer.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "tor_b200.h"
+int main(void) {
+  tor_ctx* ctx = NULL;
+  tor_camera cam;
+  double from[3] = {13, 2, 3}, at[3] = {0, 0, 0}, up[3] = {0, 1, 0};
+  tor_camera_make(&cam, from, at, up, 20.0, 16.0 / 9.0, 0.1, 10.0, 0.0, 1.0);
+  if (sizeof(tor_camera) != 192 || sizeof(tor_canvas) != 24 || sizeof(tor_hittable) != 112) return 10;
+  if (tor_random_scene(0xFACADE, 11, NULL, 0) != 485) return 11;
+  if (tor_fast_substream_count(TOR_MODE_FAST, 675, 1200, 500) != 16) return 12;
+  int rc = tor_ctx_create(NULL, 0, &ctx);
+  printf("%d %d %s\n", tor_abi_version(), rc, rc ? tor_last_error(NULL) : "ok");
+  if (rc == TOR_OK) tor_ctx_destroy(ctx);
+  return (rc == TOR_OK || rc == TOR_ERR_NO_DEVICE) ? 0 : 13;
+}
+''')
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(tor.lib_path())
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-ltor_b200", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.split()[0] == "1"
