@@ -1,5 +1,11 @@
 // tor_kernels_bvh.cuh — the sm_100a render kernel with a bounding-volume hierarchy in front of the
-// reference's sphere test (exact mode; the image is bit-identical to the brute-force scan).
+// reference's sphere test (the image is bit-identical to the brute-force scan), plus the small kernels around it:
+// the cost sort of the exact mode's pixel queue, the partial-sum reduction of the split-stream mode, draw (gamma),
+// RGB8 quantisation and the BT.601 Y'CbCr 4:2:0 conversion of the video export.
+//
+// Work units.  Exact mode: a pixel with all its samples (one RNG stream, render.nim:59-67).  Split-stream mode
+// (TOR_MODE_FAST, include/tor_b200.h): a (pixel, sample range) pair with its own counter-seeded RNG substream;
+// template parameter CHUNKED selects the warp-level queue that hands neighbouring units to the lanes of a warp.
 //
 // Why the result cannot change: the in-order scan of hittables_lists.nim:48-55 returns
 //     argmin over objects of (t_i, i),   t_i = the object's first root in (t_min, +inf)
@@ -8,8 +14,7 @@
 // closest root found so far; every object that survives is evaluated with the reference's own
 // non-fused float64 arithmetic, and ties go to the lowest original index.
 //
-// Execution model: persistent lanes, one pixel stream per lane (the reference shares one RNG stream
-// across a pixel's samples, render.nim:59-67).  The kernel alternates two phases:
+// Execution model: persistent lanes, one work unit per lane at a time.  The kernel alternates two phases:
 //   S  "shade": lanes whose traversal has finished shade the hit / the sky, start the next segment,
 //      sample or pixel (pixels come from a global atomic queue) and set up the next traversal;
 //   T  "traverse": while-while traversal (inner nodes until a leaf, then the leaf's spheres), which
