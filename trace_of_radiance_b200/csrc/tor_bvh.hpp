@@ -127,15 +127,42 @@ inline double box_area(const Box& b) {
   if (!(dx >= 0 && dy >= 0 && dz >= 0)) return 0.0;
   return 2.0 * (dx * dy + dy * dz + dz * dx);
 }
+// nextafterf(f, -inf) / nextafterf(f, +inf) for finite f (the boxes are finite by construction), on the bits
+inline float f32_pred(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) == 0u) u = 0x80000001u;  // +-0 -> smallest negative subnormal
+  else if (u & 0x80000000u) ++u;                   // negative: larger magnitude
+  else --u;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline float f32_succ(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) == 0u) u = 0x00000001u;
+  else if (u & 0x80000000u) --u;
+  else ++u;
+  memcpy(&f, &u, 4);
+  return f;
+}
 inline float f32_down(double v) {
   float f = (float)v;
-  if ((double)f > v) f = nextafterf(f, -INFINITY);
-  return nextafterf(f, -INFINITY);
+  if (!(f == f) || f - f != 0.0f) {  // NaN / inf: the library call defines the result
+    if ((double)f > v) f = nextafterf(f, -INFINITY);
+    return nextafterf(f, -INFINITY);
+  }
+  if ((double)f > v) f = f32_pred(f);
+  return f32_pred(f);
 }
 inline float f32_up(double v) {
   float f = (float)v;
-  if ((double)f < v) f = nextafterf(f, INFINITY);
-  return nextafterf(f, INFINITY);
+  if (!(f == f) || f - f != 0.0f) {
+    if ((double)f < v) f = nextafterf(f, INFINITY);
+    return nextafterf(f, INFINITY);
+  }
+  if ((double)f < v) f = f32_succ(f);
+  return f32_succ(f);
 }
 
 struct Builder {
@@ -168,19 +195,17 @@ struct Builder {
   }
 
   // Chooses a split of prims[begin, end) (count > 1); returns mid, or -1 to make a leaf.
-  int split(int begin, int end, int depth) {
+  // `all` = the union of the objects' boxes (the caller has it already).
+  int split(int begin, int end, int depth, const Box& all) {
     const int n = end - begin;
     Box cb;
     box_reset(cb);
-    Box all;
-    box_reset(all);
     for (int i = begin; i < end; ++i) {
       const Prim& p = prims[(size_t)i];
       for (int k = 0; k < 3; ++k) {
         if (p.c[k] < cb.lo[k]) cb.lo[k] = p.c[k];
         if (p.c[k] > cb.hi[k]) cb.hi[k] = p.c[k];
       }
-      box_grow(all, p.b);
     }
     int axis = 0;
     double ext = cb.hi[0] - cb.lo[0];
@@ -200,6 +225,7 @@ struct Builder {
 
     // binned surface-area heuristic on every axis
     constexpr int kBins = 16;
+    constexpr int kSmall = 24;  // object count up to which the sorted-object sweep below replaces the bin boxes
     // developer knob TOR_BVH_ISECT: cost of one sphere test relative to one node visit
     static const double c_isect_env = [] {
       const char* e = getenv("TOR_BVH_ISECT");
@@ -211,6 +237,46 @@ struct Builder {
     for (int ax = 0; ax < 3; ++ax) {
       double e = cb.hi[ax] - cb.lo[ax];
       if (!(e > 0.0)) continue;
+      if (n <= kSmall) {
+        // Few objects (most calls): the same candidates — a split after every occupied bin — evaluated on the
+        // objects sorted by bin instead of on 16 mostly empty bin boxes.  Unions and areas are exact min / max
+        // arithmetic on the same boxes and the candidates are visited in the same order, so the choice is identical.
+        const double scale = kBins / e;
+        int bin[kSmall], idx[kSmall];
+        for (int i = 0; i < n; ++i) {
+          const Prim& p = prims[(size_t)(begin + i)];
+          int b = (int)((p.c[ax] - cb.lo[ax]) * scale);
+          if (b < 0) b = 0;
+          if (b >= kBins) b = kBins - 1;
+          int j = i;  // insertion sort by bin
+          while (j > 0 && bin[j - 1] > b) {
+            bin[j] = bin[j - 1];
+            idx[j] = idx[j - 1];
+            --j;
+          }
+          bin[j] = b;
+          idx[j] = i;
+        }
+        double suffix_area[kSmall];
+        Box acc;
+        box_reset(acc);
+        for (int k = n - 1; k > 0; --k) {
+          box_grow(acc, prims[(size_t)(begin + idx[k])].b);
+          suffix_area[k] = box_area(acc);
+        }
+        box_reset(acc);
+        for (int k = 0; k < n - 1; ++k) {
+          box_grow(acc, prims[(size_t)(begin + idx[k])].b);
+          if (bin[k + 1] == bin[k]) continue;  // not a bin boundary
+          double cost = box_area(acc) * (k + 1) + suffix_area[k + 1] * (n - k - 1);
+          if (cost < best_cost) {
+            best_cost = cost;
+            best_axis = ax;
+            best_bin = bin[k];
+          }
+        }
+        continue;
+      }
       Box bb[kBins];
       int cnt[kBins];
       for (int b = 0; b < kBins; ++b) {
@@ -226,20 +292,27 @@ struct Builder {
         box_grow(bb[b], p.b);
         ++cnt[b];
       }
+      // Empty bins add nothing to a sweep: the right-hand area is carried over, and a left-hand candidate after an
+      // empty bin is the partition of the candidate before it (same cost, so never strictly better).
       double right_area[kBins];
       int right_cnt[kBins];
       Box acc;
       box_reset(acc);
       int c = 0;
+      double area = 0.0;
       for (int b = kBins - 1; b > 0; --b) {
-        box_grow(acc, bb[b]);
-        c += cnt[b];
-        right_area[b] = box_area(acc);
+        if (cnt[b]) {
+          box_grow(acc, bb[b]);
+          c += cnt[b];
+          area = box_area(acc);
+        }
+        right_area[b] = area;
         right_cnt[b] = c;
       }
       box_reset(acc);
       c = 0;
       for (int b = 0; b < kBins - 1; ++b) {
+        if (!cnt[b]) continue;
         box_grow(acc, bb[b]);
         c += cnt[b];
         if (c == 0 || right_cnt[b + 1] == 0) continue;
@@ -276,7 +349,7 @@ struct Builder {
     for (int i = begin; i < end; ++i) box_grow(*out_box, prims[(size_t)i].b);
     if (depth > max_depth) max_depth = depth;
     const int n = end - begin;
-    int mid = n == 1 ? -1 : split(begin, end, depth);
+    int mid = n == 1 ? -1 : split(begin, end, depth, *out_box);
     if (mid < 0) return make_leaf(begin, end);
     int me = (int)nodes.size();
     nodes.emplace_back();
@@ -442,7 +515,7 @@ static inline bool pack_bvh(const std::vector<tor_hittable>& objs, const tor_cam
   v.total_bytes = v.off_objs + (uint32_t)(recs.size() * sizeof(ObjRec));
   v.s_limit = bvh_detail::f32_down(1.001 * S);  // the padding was sized for origins within S (see header)
   v.max_depth = B.max_depth;
-  out->blob.assign(v.total_bytes, 0);
+  out->blob.resize(v.total_bytes);  // nodes + records cover every byte
   memcpy(out->blob.data() + v.off_nodes, nodes.data(), v.nodes_bytes);
   memcpy(out->blob.data() + v.off_objs, recs.data(), recs.size() * sizeof(ObjRec));
   out->max_depth = B.max_depth;
