@@ -248,4 +248,20 @@ int64_t bvh_check_rays(const tor_hittable* objs, int n, const tor_camera* cam, c
   return bad;
 }
 
+// FNV-1a digest of the packed BVH blob (nodes + object records): freezes the builder's output in
+// tests/test_bvh_host.py so that speed work on the builder cannot silently change the trees the kernel was tuned on.
+uint64_t bvh_blob_hash(const tor_hittable* objs, int n, const tor_camera* cam, int64_t* n_nodes) {
+  std::vector<tor_hittable> v(objs, objs + n);
+  PackedBvh pb;
+  std::string err;
+  if (!pack_bvh(v, *cam, &pb, &err)) return 0;
+  if (n_nodes) *n_nodes = pb.view.n_nodes;
+  uint64_t h = 1469598103934665603ull;
+  for (uint8_t b : pb.blob) {
+    h ^= b;
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
 }  // extern "C"

@@ -25,6 +25,8 @@ def chk():
     L.bvh_check_structure.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]
     L.bvh_check_rays.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     L.bvh_check_rays.restype = C.c_int64
+    L.bvh_blob_hash.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]
+    L.bvh_blob_hash.restype = C.c_uint64
     return L
 
 
@@ -94,3 +96,26 @@ def test_degenerate_inputs(chk, oracle):
         small = objs[1:1 + n].copy()
         assert chk.bvh_check_structure(small.ctypes.data, n, cam.ctypes.data, info) == 0
         assert chk.bvh_check_rays(small.ctypes.data, n, cam.ctypes.data, rays.ctypes.data, 5000, None) == 0
+
+
+# (scene, node count, FNV-1a of the packed blob) recorded from the builder the GPU kernel was tuned and profiled with
+FROZEN_C2_TREE = 0x1BC729B594CFFB45  # random_scene(0xFACADE, 11): 485 objects, 327 nodes
+FROZEN_TREES = {
+    0: (2, 0xE0BFDF8683103940), 1: (4, 0xA4651621F9916A30), 2: (10, 0x10374B49BA599AF2), 4: (42, 0xAB9D623490AB08B9),
+}
+
+
+def test_builder_output_is_frozen(chk, oracle):
+    """Speed work on the host-side builder must not change the trees: node and record blobs are compared by digest
+    for the small random_scene sizes, and for the larger ones against a second build (determinism)."""
+    cam = _cam(oracle)
+    for half, (nodes, digest) in FROZEN_TREES.items():
+        objs = oracle.random_scene(0xFACADE, half)
+        n = C.c_int64()
+        h = chk.bvh_blob_hash(objs.ctypes.data, len(objs), cam.ctypes.data, C.byref(n))
+        assert (n.value, h) == (nodes, digest), (half, n.value, hex(h))
+    objs = oracle.random_scene(0xFACADE, 11)
+    n = C.c_int64()
+    h11 = chk.bvh_blob_hash(objs.ctypes.data, len(objs), cam.ctypes.data, C.byref(n))
+    assert n.value == 327 and h11 == chk.bvh_blob_hash(objs.ctypes.data, len(objs), cam.ctypes.data, None)
+    assert h11 == FROZEN_C2_TREE
