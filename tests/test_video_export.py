@@ -248,6 +248,27 @@ def test_mp4_equals_the_reference_muxer(tor, oracle, tmp_path):
     assert abs(a["ticks"] / a["timescale"] - b["ticks"] / b["timescale"]) < 1e-9
 
 
+def test_mp4_three_byte_start_codes_like_the_reference_muxer(tor, oracle, tmp_path):
+    """io/mp4.nim:66-74 `get_nal_size` accepts 00 00 01 as well as 00 00 00 01.  The same stream rewritten with
+    three-byte start codes in front of the slices must give the same samples from both muxers."""
+    if not os.path.exists(REF_MUX):
+        pytest.skip("oracle/_ref/ref_mp4mux not built (needs /root/reference at build time)")
+    src = str(tmp_path / "a.264")
+    _write_264(tor, oracle, src, _test_frames(32, 48, 4))
+    data = open(src, "rb").read()
+    short = data.replace(b"\x00\x00\x00\x01\x05", b"\x00\x00\x01\x05")  # slices only; SPS / PPS keep four bytes
+    assert short != data and len(data) - len(short) == 4
+    src3 = str(tmp_path / "b.264")
+    open(src3, "wb").write(short)
+    ours, ref = str(tmp_path / "ours.mp4"), str(tmp_path / "ref.mp4")
+    tor.MP4Muxer().initialize(ours, 48, 32).writeMP4_from(src3)
+    subprocess.check_call([REF_MUX, src3, ref, "48", "32", "30"])
+    a, b, full = _mp4_summary(ours), _mp4_summary(ref), str(tmp_path / "full.mp4")
+    tor.MP4Muxer().initialize(full, 48, 32).writeMP4_from(src)
+    assert a["samples"] == b["samples"] == _mp4_summary(full)["samples"] and len(a["samples"]) == 4
+    assert a["sps"] == b["sps"] and a["pps"] == b["pps"]
+
+
 def test_mp4_decodes_with_ffmpeg(tor, oracle, tmp_path):
     cv2 = pytest.importorskip("cv2")
     src, dst = str(tmp_path / "a.264"), str(tmp_path / "a.mp4")
