@@ -234,6 +234,9 @@ struct Builder {
     const double c_trav = 1.0, c_isect = c_isect_env;
     double best_cost = INFINITY;
     int best_axis = -1, best_bin = -1;
+    Box bb3[3][kBins];  // bins of the three axes (nodes with more than kSmall objects)
+    int cnt3[3][kBins];
+    bool binned = false;
     for (int ax = 0; ax < 3; ++ax) {
       double e = cb.hi[ax] - cb.lo[ax];
       if (!(e > 0.0)) continue;
@@ -277,21 +280,31 @@ struct Builder {
         }
         continue;
       }
-      Box bb[kBins];
-      int cnt[kBins];
-      for (int b = 0; b < kBins; ++b) {
-        box_reset(bb[b]);
-        cnt[b] = 0;
+      if (!binned) {  // one pass over the objects fills the bins of all three axes
+        binned = true;
+        double scale3[3];
+        for (int k = 0; k < 3; ++k) {
+          const double ek = cb.hi[k] - cb.lo[k];
+          scale3[k] = ek > 0.0 ? kBins / ek : 0.0;  // an axis without extent is skipped above; its bins stay unused
+          for (int b = 0; b < kBins; ++b) {
+            box_reset(bb3[k][b]);
+            cnt3[k][b] = 0;
+          }
+        }
+        for (int i = begin; i < end; ++i) {
+          const Prim& p = prims[(size_t)i];
+          for (int k = 0; k < 3; ++k) {
+            if (!(scale3[k] > 0.0)) continue;
+            int b = (int)((p.c[k] - cb.lo[k]) * scale3[k]);
+            if (b < 0) b = 0;
+            if (b >= kBins) b = kBins - 1;
+            box_grow(bb3[k][b], p.b);
+            ++cnt3[k][b];
+          }
+        }
       }
-      const double scale = kBins / e;
-      for (int i = begin; i < end; ++i) {
-        const Prim& p = prims[(size_t)i];
-        int b = (int)((p.c[ax] - cb.lo[ax]) * scale);
-        if (b < 0) b = 0;
-        if (b >= kBins) b = kBins - 1;
-        box_grow(bb[b], p.b);
-        ++cnt[b];
-      }
+      const Box* bb = bb3[ax];
+      const int* cnt = cnt3[ax];
       // Empty bins add nothing to a sweep: the right-hand area is carried over, and a left-hand candidate after an
       // empty bin is the partition of the candidate before it (same cost, so never strictly better).
       double right_area[kBins];
