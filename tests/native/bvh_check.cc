@@ -248,7 +248,85 @@ int64_t bvh_check_rays(const tor_hittable* objs, int n, const tor_camera* cam, c
   return bad;
 }
 
-// FNV-1a digest of the packed BVH blob (nodes + object records): freezes the builder's output in
+// The warp-cooperative search of the render kernel (tor_kernels_bvh.cuh, COOP kernels), restated: 32 cluster boxes per
+// step, then the 32 object boxes of every cluster the ray enters, all with best_f = +inf (nothing is pruned by a
+// closer hit), then the reference's test on the survivors and the "always" list.  Returns the number of rays whose
+// closest hit differs from the full scan (must be 0).  stats[0] += box rounds, stats[1] += sphere tests.
+int64_t bvh_check_rays_coop(const tor_hittable* objs, int n, const tor_camera* cam, const double* rays, int64_t nrays,
+                            int64_t* stats) {
+  std::vector<tor_hittable> v(objs, objs + n);
+  PackedBvh pb;
+  std::string err;
+  if (!pack_bvh(v, *cam, &pb, &err)) return -1;
+  const BvhView& bv = pb.view;
+  const ObjRec* recs = (const ObjRec*)(pb.blob.data() + bv.off_objs);
+  const float* cboxes = (const float*)(pb.blob.data() + bv.off_cboxes);
+  const float* oboxes = (const float*)(pb.blob.data() + bv.off_oboxes);
+  if (bv.n_clusters != (bv.n_tree_objs + 31) / 32 || bv.ncl_pad % 32 || bv.ncl_pad < bv.n_clusters) return -2;
+  if (bv.off_oboxes != bv.off_cboxes + 24u * (uint32_t)bv.ncl_pad) return -3;
+  if (bv.hot_bytes != bv.off_oboxes + 768u * (uint32_t)bv.n_clusters || bv.off_objs != bv.hot_bytes) return -4;
+  int64_t bad = 0;
+  for (int64_t ri = 0; ri < nrays; ++ri) {
+    const double* o = rays + 7 * ri;
+    const double* d = o + 3;
+    const double time = o[6];
+    const double a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    Hit scan{INFINITY, 0xffffffffu};
+    for (int i = 0; i < bv.n_objects; ++i) better(scan, first_root(recs[i], o, d, time, a), recs[i].orig);
+
+    float df[3], of[3], id[3], oi[3];
+    for (int k = 0; k < 3; ++k) {
+      df[k] = (float)d[k];
+      of[k] = (float)o[k];
+    }
+    float dmax = fmaxf(fabsf(df[0]), fmaxf(fabsf(df[1]), fabsf(df[2])));
+    float omax = fmaxf(fabsf(of[0]), fmaxf(fabsf(of[1]), fabsf(of[2])));
+    bool ok = dmax >= 0x1p-40f && dmax <= 0x1p40f && omax <= bv.s_limit;
+    for (int k = 0; k < 3; ++k) ok = ok && df[k] == df[k] && of[k] == of[k];
+    for (int k = 0; k < 3; ++k) {
+      if (ok) {
+        float dmin = dmax * 0x1p-60f;
+        if (fabsf(df[k]) < dmin) df[k] = copysignf(dmin, df[k]);
+        id[k] = 1.0f / df[k];
+        oi[k] = of[k] * id[k];
+      } else {
+        id[k] = oi[k] = 0.f;
+      }
+    }
+    auto slab = [&](const float* base, int stride) {  // box components at base[k * stride], lo then hi
+      float t0[3], t1[3];
+      for (int k = 0; k < 3; ++k) {
+        t0[k] = fmaf(base[k * stride], id[k], -oi[k]);
+        t1[k] = fmaf(base[(3 + k) * stride], id[k], -oi[k]);
+      }
+      float nr = fmaxf(fmaxf(fminf(t0[0], t1[0]), fminf(t0[1], t1[1])), fmaxf(fminf(t0[2], t1[2]), 0.f));
+      float fr = fminf(fminf(fmaxf(t0[0], t1[0]), fmaxf(t0[1], t1[1])), fminf(fmaxf(t0[2], t1[2]), INFINITY));
+      return nr <= fr;
+    };
+    Hit best{INFINITY, 0xffffffffu};
+    for (int i = bv.n_tree_objs; i < bv.n_objects; ++i) {
+      better(best, first_root(recs[i], o, d, time, a), recs[i].orig);
+      if (stats) stats[1]++;
+    }
+    for (int c = 0; c < bv.n_clusters; ++c) {
+      if (stats && c % 32 == 0) stats[0]++;
+      if (!slab(cboxes + c, bv.ncl_pad)) continue;
+      if (stats) stats[0]++;
+      for (int i = 0; i < 32; ++i) {
+        const int obj = 32 * c + i;
+        if (obj >= bv.n_tree_objs) break;
+        if (!slab(oboxes + (size_t)c * 192 + i, 32)) continue;
+        better(best, first_root(recs[obj], o, d, time, a), recs[obj].orig);
+        if (stats) stats[1]++;
+      }
+    }
+    if (!(best.t == scan.t && (best.orig == scan.orig || scan.t == INFINITY))) ++bad;
+  }
+  return bad;
+}
+
+// FNV-1a digest of the packed BVH blob's nodes and object records (the box tables of the cooperative search are
+// derived from the same boxes and checked by bvh_check_rays_coop): freezes the builder's output in
 // tests/test_bvh_host.py so that speed work on the builder cannot silently change the trees the kernel was tuned on.
 uint64_t bvh_blob_hash(const tor_hittable* objs, int n, const tor_camera* cam, int64_t* n_nodes) {
   std::vector<tor_hittable> v(objs, objs + n);
@@ -257,10 +335,14 @@ uint64_t bvh_blob_hash(const tor_hittable* objs, int n, const tor_camera* cam, i
   if (!pack_bvh(v, *cam, &pb, &err)) return 0;
   if (n_nodes) *n_nodes = pb.view.n_nodes;
   uint64_t h = 1469598103934665603ull;
-  for (uint8_t b : pb.blob) {
-    h ^= b;
-    h *= 1099511628211ull;
-  }
+  auto feed = [&](size_t begin, size_t end) {
+    for (size_t i = begin; i < end; ++i) {
+      h ^= pb.blob[i];
+      h *= 1099511628211ull;
+    }
+  };
+  feed(pb.view.off_nodes, pb.view.off_nodes + (size_t)pb.view.n_nodes * sizeof(BvhNode));
+  feed(pb.view.off_objs, pb.view.total_bytes);
   return h;
 }
 

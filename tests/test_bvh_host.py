@@ -25,6 +25,8 @@ def chk():
     L.bvh_check_structure.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]
     L.bvh_check_rays.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     L.bvh_check_rays.restype = C.c_int64
+    L.bvh_check_rays_coop.argtypes = L.bvh_check_rays.argtypes
+    L.bvh_check_rays_coop.restype = C.c_int64
     L.bvh_blob_hash.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]
     L.bvh_blob_hash.restype = C.c_uint64
     return L
@@ -70,6 +72,10 @@ def test_rays_reach_every_hit_object(chk, oracle):
     stats = (C.c_int64 * 2)()
     assert chk.bvh_check_rays(objs.ctypes.data, len(objs), cam.ctypes.data, rays.ctypes.data, len(rays), stats) == 0
     assert stats[1] < 0.05 * len(rays) * len(objs)  # the hierarchy actually prunes
+    # the box tables of the warp-cooperative search reach the same hits, with few candidates per ray
+    cstats = (C.c_int64 * 2)()
+    assert chk.bvh_check_rays_coop(objs.ctypes.data, len(objs), cam.ctypes.data, rays.ctypes.data, len(rays), cstats) == 0
+    assert cstats[1] < 0.05 * len(rays) * len(objs)
 
 
 def test_degenerate_inputs(chk, oracle):
@@ -91,11 +97,13 @@ def test_degenerate_inputs(chk, oracle):
     rays[::13, 3:6] *= 1e-20  # outside the float32 range the padding was derived for: "test everything" route
     rays[::17, 3:6] = np.nan
     assert chk.bvh_check_rays(objs.ctypes.data, len(objs), cam.ctypes.data, rays.ctypes.data, len(rays), None) == 0
+    assert chk.bvh_check_rays_coop(objs.ctypes.data, len(objs), cam.ctypes.data, rays.ctypes.data, len(rays), None) == 0
     # single object and two objects: degenerate trees
     for n in (1, 2):
         small = objs[1:1 + n].copy()
         assert chk.bvh_check_structure(small.ctypes.data, n, cam.ctypes.data, info) == 0
         assert chk.bvh_check_rays(small.ctypes.data, n, cam.ctypes.data, rays.ctypes.data, 5000, None) == 0
+        assert chk.bvh_check_rays_coop(small.ctypes.data, n, cam.ctypes.data, rays.ctypes.data, 5000, None) == 0
 
 
 # (scene, node count, FNV-1a of the packed blob) recorded from the builder the GPU kernel was tuned and profiled with

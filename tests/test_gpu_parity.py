@@ -327,3 +327,78 @@ def test_cost_ranked_pixel_queue(tor, oracle, gpu_ctx, h, w, spp, rows):
     pixels than lanes, pixel counts that are not a multiple of the CTA size, row subsets, and more pixels than one
     CTA wave."""
     _check(tor, oracle, gpu_ctx, tor.random_scene().list(), _book_cam(tor), h, w, spp, rows=rows)
+
+
+# ---------------------------------------------------------------------------------- warp-cooperative pixels
+class _EnvCtx:
+    """A context created under developer knobs (they are read once, at tor_ctx_create)."""
+
+    def __init__(self, tor, **env):
+        self.tor, self.env, self.ctx, self.old = tor, {k: str(v) for k, v in env.items()}, None, {}
+
+    def __enter__(self):
+        for k, v in self.env.items():
+            self.old[k] = os.environ.get(k)
+            os.environ[k] = v
+        self.ctx = self.tor.Context()
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        return self.ctx
+
+    def __exit__(self, *a):
+        self.ctx.close()
+
+
+@pytest.mark.parametrize("force", [10 ** 9, 37])
+def test_cooperative_pixels_bit_exact(tor, oracle, force):
+    """The warp-cooperative route (one warp traces one expensive pixel, tor_kernels_bvh.cuh) forced onto every pixel
+    of the launch (force = 10^9) or onto the 37 most expensive ones beside the ordinary lanes: same bits as the
+    oracle for the book scene, hand-made scenes (ties, degenerate movers, hollow glass), random mixes, 1 601 and
+    10 002 spheres, row subsets and canvases smaller than a warp's worth of clusters."""
+    with _EnvCtx(tor, TOR_BVH_PREPASS_SPP=9, TOR_BVH_COOP_FORCE=force) as ctx:
+        world, cam = tor.random_scene().list(), _book_cam(tor)
+        _check(tor, oracle, ctx, world, cam, 36, 64, 10)
+        _check(tor, oracle, ctx, world, cam, 54, 96, 12, rows=(5, 41, 7))
+        _check(tor, oracle, ctx, world, cam, 9, 11, 9)
+        for name, w in _handmade_scenes(tor).items():
+            _check(tor, oracle, ctx, w, cam, 30, 40, 10)
+            inside = tor.camera((0, 0.3, 2.5), (0, 0.2, -1), (0, 1, 0), 60.0, 4 / 3, 0.0, 1.0, -0.5, 2.5)
+            _check(tor, oracle, ctx, w, inside, 30, 40, 10)
+        an = oracle.Animation(height=36, width=64, t_max=9.0)
+        cam_arr, objs = an.next_frame(skip=6)
+        _check(tor, oracle, ctx, tor.HittableList(objs), tor.Camera.from_array(cam_arr), 36, 64, 9)
+        big = tor.random_scene(0xFACADE, 50).list()
+        _check(tor, oracle, ctx, big, cam, 18, 32, 9)
+        # depth edges inside the cooperative loop
+        for depth in (1, 2):
+            cv = tor.newCanvas(20, 30, 9, 2.2)
+            ctx.render(cv, cam, world, depth)
+            ref = oracle.render(20, 30, 9, cam.as_array(), world.objects, max_depth=depth, math="det")
+            assert cv.pixels.tobytes() == ref.tobytes()
+
+
+def test_cooperative_pixels_c1_digest(tor):
+    """All of C1 through the cooperative route: the frozen sha256 of the oracle's float64 framebuffer."""
+    with _EnvCtx(tor, TOR_BVH_PREPASS_SPP=9, TOR_BVH_COOP_FORCE=10 ** 9) as ctx:
+        cv = tor.newCanvas(216, 384, 100, 2.2)
+        ctx.render(cv, _book_cam(tor), tor.random_scene().list(), 50)
+        digest = json.load(open(os.path.join(GOLD, "c1_oracle_digest.json")))
+        assert hashlib.sha256(cv.pixels.tobytes()).hexdigest() == digest["det"]["f64_sha256"]
+
+
+def test_cooperative_pixels_default_policy_on_a_gpu_share_of_c2(tor, oracle, gpu_ctx):
+    """An eighth of C2's rows (one GPU's share of an 8-GPU render) with the default policy — the cost pre-pass picks
+    the cooperative pixels itself — against the same rows of the brute-force scan, and one row against the oracle."""
+    world, cam = tor.random_scene().list(), _book_cam(tor)
+    h, w, spp = 675, 1200, 500
+    a = tor.newCanvas(h, w, spp, 2.2)
+    b = tor.newCanvas(h, w, spp, 2.2)
+    gpu_ctx.render(a, cam, world, 50, rows=(3, h, 8))
+    gpu_ctx.render(b, cam, world, 50, rows=(3, h, 8), flags=tor.api.TOR_FLAG_ROW_MAJOR_QUEUE)
+    assert a.pixels.tobytes() == b.pixels.tobytes()
+    ref = np.zeros((h, w, 3))
+    oracle.render(h, w, spp, cam.as_array(), world.objects, rows=(203, 204, 1), math="det", out=ref)
+    assert a.pixels[203].tobytes() == ref[203].tobytes()

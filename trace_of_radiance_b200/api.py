@@ -57,7 +57,7 @@ EXPORTED_SYMBOLS = [
     "tor_launch_count", "tor_measure_fp64_peak", "tor_get_traversal_counters", "tor_scene_info", "tor_camera_make", "tor_random_scene", "tor_export_ppm", "tor_quantise_rgb8", "tor_animation_create",
     "tor_animation_next_frame", "tor_animation_destroy", "tor_render_rgb8", "tor_render_rgb8_async", "tor_host_alloc",
     "tor_host_free", "tor_render_ycbcr420", "tor_render_ycbcr420_async", "tor_h264_open", "tor_h264_frame_buffer",
-    "tor_h264_flush_frame", "tor_h264_finish", "tor_mp4_mux_h264_file", "tor_fast_substream_count",
+    "tor_h264_flush_frame", "tor_h264_finish", "tor_mp4_mux_h264_file", "tor_fast_substream_count", "tor_last_schedule",
 ]
 
 
@@ -128,6 +128,7 @@ def load_library():
     L.tor_get_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.tor_get_traversal_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.tor_scene_info.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.tor_last_schedule.argtypes = [vp, C.POINTER(C.c_int64)]
     L.tor_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.tor_launch_count.argtypes = [vp]
     L.tor_launch_count.restype = C.c_int64
@@ -424,6 +425,13 @@ class Context:
         self._check(self.L.tor_scene_info(self.h, out))
         keys = ("objects", "bvh_nodes", "bvh_leaves", "bvh_depth", "objects_outside_tree", "bvh_bytes")
         return dict(zip(keys, (int(v) for v in out)))
+
+    def last_schedule(self):
+        """Pixel scheduling of the last exact-mode render with a cost pre-pass (tor_last_schedule)."""
+        out = (C.c_int64 * 4)()
+        self._check(self.L.tor_last_schedule(self.h, out))
+        return {"cooperative_pixels": int(out[0]), "qualifying_pixels": int(out[1]), "prepass_segments": int(out[2]),
+                "devices": int(out[3])}
 
     def last_kernel_ms(self):
         ms = C.c_float()

@@ -21,6 +21,62 @@ namespace {
 
 constexpr int kBlock = 256;
 
+// Developer tuning knobs of the BVH route, read from the environment ONCE, when a context is created (DESIGN.md
+// lists them).  None of them can change an image: they only move work between lanes, warps and launches.
+struct Tuning {
+  int block = kBlock;          // TOR_BVH_BLOCK: CTA size, 256 (two CTAs per SM) or 512 (one)
+  int refill = 20;             // TOR_BVH_REFILL: waiting lanes of a warp that trigger a shade phase (exact mode)
+  int refill_fast = 20;        // TOR_BVH_REFILL_FAST: the same in split-stream mode
+  int chunk = 0;               // TOR_BVH_CHUNK: queue slots per warp-level fetch (0 = default rule)
+  int lanes = 32;              // TOR_BVH_LANES: lanes of each warp that take pixels
+  bool deal = true;            // TOR_BVH_EXACT_DEAL=0: queue every ranked pixel, no dealt first wave
+  int deal_group = 8;          // TOR_BVH_DEAL_GROUP: lanes per cost tier of the dealt wave
+  bool queue_percost = false;  // TOR_BVH_EXACT_QUEUE=percost: one class per cost value, one atomic per lane
+  bool no_scramble = false;    // TOR_BVH_NO_SCRAMBLE: row-major queue for renders without a cost pre-pass
+  bool fast_scramble = false;  // TOR_BVH_FAST_SCRAMBLE: scattered queue in split-stream mode
+  float coop_alpha = 2.0f;     // TOR_BVH_COOP_ALPHA: a pixel is traced by a whole warp when its pre-pass cost
+                               //   exceeds alpha x the mean cost per lane of the launch
+  int coop_max_pct = 25;       // TOR_BVH_COOP_MAX: at most this percentage of the grid's warps start cooperatively
+                               //   (0 switches the mechanism off)
+  long long coop_force = -1;   // TOR_BVH_COOP_FORCE: trace exactly this many of the most expensive pixels
+                               //   cooperatively (tests), still capped by coop_max_pct
+  int prepass_min_spp = 256;   // TOR_BVH_PREPASS_SPP: samples per pixel from which the cost pre-pass runs
+
+  static Tuning from_env() {
+    Tuning t;
+    auto geti = [](const char* name, int dflt) {
+      const char* e = getenv(name);
+      return e ? atoi(e) : dflt;
+    };
+    auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    t.block = geti("TOR_BVH_BLOCK", kBlock) == 512 ? 512 : kBlock;
+    t.refill = clampi(geti("TOR_BVH_REFILL", 20), 1, 32);
+    t.refill_fast = clampi(geti("TOR_BVH_REFILL_FAST", 20), 1, 32);
+    {
+      int c = geti("TOR_BVH_CHUNK", 0);
+      t.chunk = c <= 0 ? 0 : (c < 32 ? 32 : (c > 4096 ? 4096 : c / 32 * 32));
+    }
+    t.lanes = clampi(geti("TOR_BVH_LANES", 32), 1, 32);
+    t.deal = geti("TOR_BVH_EXACT_DEAL", 1) != 0;
+    {
+      int g = geti("TOR_BVH_DEAL_GROUP", 8);
+      t.deal_group = (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) ? g : 8;
+    }
+    {
+      const char* e = getenv("TOR_BVH_EXACT_QUEUE");
+      t.queue_percost = e && strcmp(e, "percost") == 0;
+    }
+    t.no_scramble = getenv("TOR_BVH_NO_SCRAMBLE") != nullptr;
+    t.fast_scramble = getenv("TOR_BVH_FAST_SCRAMBLE") != nullptr;
+    if (const char* e = getenv("TOR_BVH_COOP_ALPHA")) t.coop_alpha = (float)atof(e);
+    if (!(t.coop_alpha > 0.f)) t.coop_alpha = 2.0f;
+    t.coop_max_pct = clampi(geti("TOR_BVH_COOP_MAX", 25), 0, 50);
+    if (const char* e = getenv("TOR_BVH_COOP_FORCE")) t.coop_force = atoll(e);
+    t.prepass_min_spp = clampi(geti("TOR_BVH_PREPASS_SPP", 256), 9, 1 << 30);
+    return t;
+  }
+};
+
 struct DeviceState {
   int dev = 0;
   int sm_count = 0;
@@ -28,14 +84,22 @@ struct DeviceState {
   int max_smem_per_sm = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  uint8_t* d_blob = nullptr;  // [brute-force scene blob | BVH blob], each 128-byte aligned
+  cudaEvent_t ev_busy = nullptr;  // end of the last launch that used this device's scratch buffers (any stream)
+  bool busy = false;
+  uint8_t* d_blob = nullptr;  // BVH blob (tor_bvh.hpp)
   size_t blob_cap = 0;
+  uint8_t* d_brute = nullptr;  // brute-force route's scene blob (tor_scene_pack.hpp), uploaded on first use
+  size_t brute_cap = 0;
+  bool brute_current = false;
   double* d_pixels = nullptr;
   size_t pix_cap = 0;  // bytes
   unsigned long long* d_work = nullptr;      // pixel queue heads: [0] render, [1] cost pre-pass
   uint32_t* d_cost = nullptr;                // per-pixel cost of the pre-pass, then the bucket offsets
   uint32_t* d_order = nullptr;               // pixel queue order (most expensive first)
   uint32_t* d_hist = nullptr;                // kCostBuckets counters
+  uint32_t* d_sched = nullptr;               // [0] cooperative pixels of the launch (BvhRenderParams::sched)
+  uint32_t* d_coop = nullptr;                // the cooperative pixels, most expensive first
+  size_t coop_cap = 0;                       // entries
   double* d_partial = nullptr;               // split-stream mode: one partial sum (3 doubles) per (pixel, range)
   size_t partial_cap = 0;                    // bytes
   uint8_t* d_rgb8 = nullptr;                 // packed RGB8 image of tor_render_rgb8
@@ -51,15 +115,17 @@ struct DeviceState {
 struct tor_ctx {
   std::vector<DeviceState> devs;
   std::string err;
-  tor::PackedScene scene;
+  std::vector<tor_hittable> objs;  // the scene as decoded flat records (host copy; the caller's buffer is not kept)
+  tor::PackedScene scene;          // brute-force route only: packed on first use (ensure_brute_scene)
+  bool brute_packed = false;
   tor::PackedBvh bvh;
-  size_t bvh_off = 0;  // offset of the BVH blob inside the device blob
   tor_camera cam;
   bool have_scene = false;
   int64_t launches = 0;
   uint64_t counters[3] = {0, 0, 0};
   uint64_t trav_counters[2] = {0, 0};
   bool counters_pending = false;
+  Tuning tune;
 };
 
 namespace {
@@ -107,35 +173,24 @@ LaunchPlan plan_for(const tor::SceneView& sv, int max_smem_optin) {
 }
 
 // The hierarchy is staged in shared memory only while two CTAs still fit on an SM (the traversal is
-// latency-bound and wants the warps); beyond that the nodes, then nothing, and L1/L2 serve the rest.
-template <int B, bool CHUNKED>
+// latency-bound and wants the warps); beyond that the nodes and box tables, then nothing, and L1/L2 serve the rest.
+template <int B, bool CHUNKED, bool COOP>
 BvhLaunchPlan bvh_plan_b(const tor::BvhView& bv, size_t budget) {
-  if (bv.total_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<B, 2, CHUNKED>, 2, bv.total_bytes, B};
-  if (bv.nodes_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<B, 1, CHUNKED>, 1, bv.nodes_bytes, B};
-  return BvhLaunchPlan{tor::render_bvh_kernel<B, 0, CHUNKED>, 0, 0, B};
+  if (bv.total_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<B, 2, CHUNKED, COOP>, 2, bv.total_bytes, B};
+  if (bv.hot_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<B, 1, CHUNKED, COOP>, 1, bv.hot_bytes, B};
+  return BvhLaunchPlan{tor::render_bvh_kernel<B, 0, CHUNKED, COOP>, 0, 0, B};
 }
 
-// chunked: the warp-level queue of the split-stream mode (tor_kernels_bvh.cuh); otherwise one atomic per lane
-BvhLaunchPlan bvh_plan_for(const tor::BvhView& bv, int max_smem_per_sm, int max_smem_optin, bool chunked) {
-  static const int block = [] {  // developer tuning knob: CTA size 256 (two CTAs per SM) or 512 (one)
-    const char* e = getenv("TOR_BVH_BLOCK");
-    return e ? atoi(e) : kBlock;
-  }();
-  const size_t half = (size_t)max_smem_per_sm / 2 - 2048;
-  const size_t whole = (size_t)max_smem_optin;
-  if (block == 512) return chunked ? bvh_plan_b<512, true>(bv, whole) : bvh_plan_b<512, false>(bv, whole);
-  return chunked ? bvh_plan_b<kBlock, true>(bv, half) : bvh_plan_b<kBlock, false>(bv, half);
-}
-
-// kRefill of the BVH kernel (tor_kernels_bvh.cuh).  The environment variable is a developer tuning knob;
-// the default is the measured optimum on B200 for C2.
-int bvh_refill() {
-  static const int v = [] {
-    const char* e = getenv("TOR_BVH_REFILL");
-    int r = e ? atoi(e) : 20;
-    return r < 1 ? 1 : (r > 32 ? 32 : r);
-  }();
-  return v;
+// chunked: the warp-level queue (tor_kernels_bvh.cuh); otherwise one atomic per lane.  coop: the variant with the
+// warp-cooperative pixels (exact mode with a cost-ranked order only; always chunked).
+BvhLaunchPlan bvh_plan_for(const tor::BvhView& bv, int max_smem_per_sm, int max_smem_optin, bool chunked, bool coop,
+                           int block) {
+  // per CTA: the dynamic part + ~1.4 KB of static shared memory + 1 KB the system reserves
+  const size_t half = (size_t)max_smem_per_sm / 2 - 4096;
+  const size_t whole = (size_t)max_smem_optin - 2048;
+  if (block == 512) return chunked ? bvh_plan_b<512, true, false>(bv, whole) : bvh_plan_b<512, false, false>(bv, whole);
+  if (coop) return bvh_plan_b<kBlock, true, true>(bv, half);
+  return chunked ? bvh_plan_b<kBlock, true, false>(bv, half) : bvh_plan_b<kBlock, false, false>(bv, half);
 }
 
 // A multiplier m coprime to n with m/n near the golden ratio: i -> i*m mod n is a bijection of [0, n) that sends
@@ -155,7 +210,7 @@ uint32_t coprime_near_golden(uint32_t n) {
   return (uint32_t)(m % n);
 }
 
-size_t device_blob_bytes(const tor_ctx* ctx) { return ctx->bvh_off + ctx->bvh.blob.size(); }
+size_t device_blob_bytes(const tor_ctx* ctx) { return ctx->bvh.blob.size(); }
 
 int ensure_capacity(tor_ctx* ctx, DeviceState& d, size_t blob_bytes, size_t pix_bytes) {
   TOR_CUDA(ctx, cudaSetDevice(d.dev));
@@ -177,17 +232,58 @@ int ensure_capacity(tor_ctx* ctx, DeviceState& d, size_t blob_bytes, size_t pix_
   return TOR_OK;
 }
 
+// Renders launched on a caller's stream (tor_render_device_async) may still read this device's scene blobs and
+// scratch arrays: wait for the last one before anything is overwritten from the host side.
+int wait_idle(tor_ctx* ctx, DeviceState& d) {
+  if (d.busy) {
+    TOR_CUDA(ctx, cudaSetDevice(d.dev));
+    TOR_CUDA(ctx, cudaEventSynchronize(d.ev_busy));
+    d.busy = false;
+  }
+  return TOR_OK;
+}
+
 int upload_scene_to(tor_ctx* ctx, DeviceState& d) {
   if (d.scene_current) return TOR_OK;
-  int rc = ensure_capacity(ctx, d, device_blob_bytes(ctx), 0);
+  int rc = wait_idle(ctx, d);
   if (rc) return rc;
-  TOR_CUDA(ctx, cudaMemcpyAsync(d.d_blob, ctx->scene.blob.data(), ctx->scene.blob.size(), cudaMemcpyHostToDevice,
-                                d.stream));
-  TOR_CUDA(ctx, cudaMemcpyAsync(d.d_blob + ctx->bvh_off, ctx->bvh.blob.data(), ctx->bvh.blob.size(),
-                                cudaMemcpyHostToDevice, d.stream));
-  // the blob vectors may be rebuilt by the next tor_scene_upload: finish the copies before returning
+  rc = ensure_capacity(ctx, d, device_blob_bytes(ctx), 0);
+  if (rc) return rc;
+  TOR_CUDA(ctx, cudaMemcpyAsync(d.d_blob, ctx->bvh.blob.data(), ctx->bvh.blob.size(), cudaMemcpyHostToDevice, d.stream));
+  // the blob vector may be rebuilt by the next tor_scene_upload: finish the copy before returning
   TOR_CUDA(ctx, cudaStreamSynchronize(d.stream));
   d.scene_current = true;
+  return TOR_OK;
+}
+
+// The brute-force route's scene blob (filter records, tor_scene_pack.hpp) is built and uploaded on first use only:
+// the default BVH route never pays for it (an animation re-sets the scene every frame).
+int upload_brute_scene_to(tor_ctx* ctx, DeviceState& d) {
+  if (!ctx->brute_packed) {
+    if (ctx->objs.size() > 65535)
+      return fail(ctx, TOR_ERR_SCENE_TOO_LARGE, "TOR_FLAG_BRUTE_FORCE: more than 65535 objects (16-bit indices)");
+    std::string err;
+    if (!tor::pack_scene(ctx->objs.data(), (int64_t)ctx->objs.size(), TOR_STRIDE_FLAT, ctx->cam.shutter_open,
+                         ctx->cam.shutter_close, &ctx->scene, &err))
+      return fail(ctx, TOR_ERR_INVALID_ARG, err);
+    ctx->brute_packed = true;
+    for (DeviceState& o : ctx->devs) o.brute_current = false;
+  }
+  if (d.brute_current) return TOR_OK;
+  int rc = wait_idle(ctx, d);
+  if (rc) return rc;
+  TOR_CUDA(ctx, cudaSetDevice(d.dev));
+  if (ctx->scene.blob.size() > d.brute_cap) {
+    if (d.d_brute) cudaFree(d.d_brute);
+    d.d_brute = nullptr;
+    d.brute_cap = 0;
+    TOR_CUDA(ctx, cudaMalloc(&d.d_brute, ctx->scene.blob.size()));
+    d.brute_cap = ctx->scene.blob.size();
+  }
+  TOR_CUDA(ctx, cudaMemcpyAsync(d.d_brute, ctx->scene.blob.data(), ctx->scene.blob.size(), cudaMemcpyHostToDevice,
+                                d.stream));
+  TOR_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  d.brute_current = true;
   return TOR_OK;
 }
 
@@ -197,25 +293,18 @@ int set_scene(tor_ctx* ctx, const tor_camera* cam, const void* objects, int64_t 
     return fail(ctx, TOR_ERR_INVALID_ARG, "empty HittableList (hittables_lists.nim:42 asserts len > 0)");
   if (stride != TOR_STRIDE_FLAT && stride != TOR_STRIDE_NIM_VARIANT)
     return fail(ctx, TOR_ERR_LAYOUT, "stride must be 112 (tor_hittable) or 120 (Nim HittableVariant)");
-  if (len > 65535) return fail(ctx, TOR_ERR_SCENE_TOO_LARGE, "more than 65535 objects");
+  if (len > tor::kBvhMaxObjects) return fail(ctx, TOR_ERR_SCENE_TOO_LARGE, "more than 16777216 objects");
+  ctx->have_scene = false;
+  ctx->brute_packed = false;
+  ctx->objs.resize((size_t)len);
+  for (int64_t i = 0; i < len; ++i)
+    if (!tor::decode_object((const uint8_t*)objects + i * stride, stride, &ctx->objs[(size_t)i]))
+      return fail(ctx, TOR_ERR_INVALID_ARG, "object " + std::to_string(i) + ": unknown kind / material tag");
   std::string err;
-  if (!tor::pack_scene(objects, len, stride, cam->shutter_open, cam->shutter_close, &ctx->scene, &err)) {
-    ctx->have_scene = false;
-    return fail(ctx, TOR_ERR_INVALID_ARG, err);
-  }
-  {
-    std::vector<tor_hittable> objs((size_t)len);
-    for (int64_t i = 0; i < len; ++i)
-      tor::decode_object((const uint8_t*)objects + i * stride, stride, &objs[(size_t)i]);  // validated by pack_scene
-    if (!tor::pack_bvh(objs, *cam, &ctx->bvh, &err)) {
-      ctx->have_scene = false;
-      return fail(ctx, TOR_ERR_INVALID_ARG, err);
-    }
-  }
-  ctx->bvh_off = (ctx->scene.blob.size() + 127) / 128 * 128;
+  if (!tor::pack_bvh(ctx->objs, *cam, &ctx->bvh, &err)) return fail(ctx, TOR_ERR_INVALID_ARG, err);
   ctx->cam = *cam;
   ctx->have_scene = true;
-  for (DeviceState& d : ctx->devs) d.scene_current = false;
+  for (DeviceState& d : ctx->devs) d.scene_current = d.brute_current = false;
   return TOR_OK;
 }
 
@@ -274,13 +363,18 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       return fail(ctx, TOR_ERR_INVALID_ARG, "TOR_MODE_FAST: more than 2^32 (pixel, range) units in one launch");
   }
   const unsigned long long want = (total_px + kBlock - 1) / kBlock;
+  if (d.busy) TOR_CUDA(ctx, cudaStreamWaitEvent(stream, d.ev_busy, 0));  // previous launch may be on another stream
   TOR_CUDA(ctx, cudaMemsetAsync(d.d_work, 0, 2 * sizeof(unsigned long long), stream));
 
   if (flags & TOR_FLAG_BRUTE_FORCE) {
     tor::RenderParams P;
     memset(&P, 0, sizeof(P));
+    {
+      int rc = upload_brute_scene_to(ctx, d);
+      if (rc) return rc;
+    }
     P.sv = ctx->scene.view;
-    P.blob = d.d_blob;
+    P.blob = d.d_brute;
     P.cam = ctx->cam;
     P.pixels = d_out;
     P.nrows = nrows;
@@ -307,10 +401,11 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     if (timed) TOR_CUDA(ctx, cudaEventRecord(d.ev0, stream));
     plan.fn<<<grid, kBlock, plan.smem, stream>>>(P);
   } else {
+    const Tuning& tune = ctx->tune;
     tor::BvhRenderParams P;
     memset(&P, 0, sizeof(P));
     P.bv = ctx->bvh.view;
-    P.blob = d.d_blob + ctx->bvh_off;
+    P.blob = d.d_blob;
     P.cam = ctx->cam;
     P.pixels = d_out;
     P.nrows = nrows;
@@ -325,21 +420,14 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     P.count_segments = count ? 1u : 0u;
     P.work_counter = d.d_work;
     P.counters = d.d_counters;
-    P.refill = bvh_refill();
-    P.lanes_per_warp = 32;
-    {
-      static const int chunk_env = [] {  // developer tuning knob: queue slots per warp-level fetch (0 = default rule)
-        const char* e = getenv("TOR_BVH_CHUNK");
-        int c = e ? atoi(e) : 0;
-        return c <= 0 ? 0 : (c < 32 ? 32 : (c > 4096 ? 4096 : c / 32 * 32));
-      }();
-      P.chunk = (uint32_t)chunk_env;
-    }
-    if (P.refill > P.lanes_per_warp) P.refill = P.lanes_per_warp;
+    P.refill = tune.refill;
+    P.lanes_per_warp = tune.lanes;
+    P.chunk = (uint32_t)tune.chunk;
 
-    BvhLaunchPlan plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin, /*chunked=*/sub_log2 != 0);
+    BvhLaunchPlan plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin, /*chunked=*/sub_log2 != 0,
+                                      /*coop=*/false, tune.block);
     const int block = plan.block;
-    BvhLaunchPlan main_plan = plan;  // the cost pre-pass always runs `plan`; the main launch may use the chunked queue
+    BvhLaunchPlan main_plan = plan;  // the cost pre-pass always runs `plan`; the main launch may use another variant
     TOR_CUDA(ctx, cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     int per_sm = 0;
     TOR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, block, plan.smem));
@@ -351,8 +439,9 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
 
     // Pixel scheduling.  A pixel's samples are a serial chain, so the order in which pixels start
     // decides when the render ends.  With enough samples per pixel a cost pre-pass (the first `pre` samples of every
-    // pixel, only their segment counts kept) ranks the pixels; the most expensive ones are dealt to the lanes so that
-    // every warp starts with the same mix of costs, the rest is queued most-expensive-first.
+    // pixel, only their segment counts kept) ranks the pixels; the few most expensive ones are traced by a whole warp
+    // each, the next ones are dealt to the lanes so that every warp starts with the same mix of costs, the rest is
+    // queued most-expensive-first.
     const unsigned long long lanes = (unsigned long long)grid * block;
     // Split-stream queue: a warp takes 64 consecutive units at a time when every lane gets plenty of them, 32 (one
     // per lane) otherwise and over the last four units per lane, so that no warp ends the render on a long chunk of
@@ -361,7 +450,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     if (P.chunk == 0) P.chunk = (total_px << sub_log2) >= lanes * 64ull ? 64u : 32u;
     // below 256 spp the pre-pass costs more than the order gains (C1: +1 ms); split-stream units are short and
     // plentiful, so they need no ranking either
-    const int32_t pre = (spp >= 256 && sub_log2 == 0) ? 8 : 0;
+    const int32_t pre = (spp >= tune.prepass_min_spp && sub_log2 == 0) ? 8 : 0;
     if (sub_log2) {
       const size_t need = (size_t)(total_px << sub_log2) * 3 * sizeof(double);
       if (need > d.partial_cap) {
@@ -376,32 +465,18 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     }
     const bool reorder = !(flags & TOR_FLAG_ROW_MAJOR_QUEUE) && total_px > 64 && total_px < 0x7fffffffull &&
                          max_depth > 0;
-    if (const char* e = getenv("TOR_BVH_LANES")) {  // developer tuning knob
-      int v = atoi(e);
-      P.lanes_per_warp = v < 1 ? 1 : (v > 32 ? 32 : v);
-    }
     if (P.refill > (P.lanes_per_warp * 5) / 8) P.refill = (P.lanes_per_warp * 5) / 8;
     if (sub_log2) {
       // split-stream mode: the lanes of a warp trace neighbouring rays and finish their traversals close together,
       // so waiting for more of them before shading costs little and shades more lanes at once
-      static const int fast_refill = [] {  // developer tuning knob
-        const char* e = getenv("TOR_BVH_REFILL_FAST");
-        int r = e ? atoi(e) : 20;
-        return r < 1 ? 1 : (r > 32 ? 32 : r);
-      }();
-      P.refill = fast_refill < P.lanes_per_warp ? fast_refill : P.lanes_per_warp;
+      P.refill = tune.refill_fast < P.lanes_per_warp ? tune.refill_fast : P.lanes_per_warp;
     }
     if (P.refill < 1) P.refill = 1;
     if (reorder && pre > 0 && P.lanes_per_warp == 32 && (block % 32) == 0) {
-      static const bool deal = [] {  // developer knob: TOR_BVH_EXACT_DEAL=0 queues every pixel (no dealt first wave)
-        const char* e = getenv("TOR_BVH_EXACT_DEAL");
-        return !(e && atoi(e) == 0);
-      }();
-      const uint32_t warps = deal ? (uint32_t)(lanes / 32) : 0u;
-      const uint32_t first_wave = warps * 32u;
+      const uint32_t warps_all = (uint32_t)(lanes / 32);
+      const uint32_t warps = tune.deal ? warps_all : 0u;  // warps that are dealt a first wave
       const uint32_t n = (uint32_t)total_px;
-      const uint32_t n_first = n < first_wave ? n : first_wave;
-      const size_t slots = (size_t)first_wave + (n - n_first);
+      const size_t slots = (size_t)warps * 32u + n;  // upper bound of [dealt][queue] for any cooperative count
       if (slots > d.order_cap) {
         if (d.d_cost) cudaFree(d.d_cost);
         if (d.d_order) cudaFree(d.d_order);
@@ -410,6 +485,26 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
         TOR_CUDA(ctx, cudaMalloc(&d.d_cost, slots * sizeof(uint32_t)));
         TOR_CUDA(ctx, cudaMalloc(&d.d_order, slots * sizeof(uint32_t)));
         d.order_cap = slots;
+      }
+      // Queue order: most expensive class first.  Default: coarse classes with the image order kept inside a class
+      // and warps that take 32 consecutive queue entries at a time (the CHUNKED kernel), so that after the dealt
+      // first wave the lanes of a warp work on neighbouring pixels of the same kind.  TOR_BVH_EXACT_QUEUE=percost
+      // selects the earlier scheme (one class per cost value, arbitrary order inside, one atomic per lane).
+      const bool coherent = !tune.queue_percost;
+      // Warp-cooperative pixels: only in the default scheme, with the dealt wave, and never more than half the warps.
+      // (TOR_BVH_COOP_FORCE lifts the cap to every pixel of the launch: the parity tests run whole images that way.)
+      uint32_t coop_max = 0;
+      if (coherent && warps && block == kBlock) {
+        coop_max = (uint32_t)((unsigned long long)warps_all * (unsigned)tune.coop_max_pct / 100ull);
+        if (coop_max > warps_all / 2) coop_max = warps_all / 2;
+        if (tune.coop_force >= 0 && tune.coop_max_pct > 0) coop_max = n;
+      }
+      if (coop_max > d.coop_cap) {
+        if (d.d_coop) cudaFree(d.d_coop);
+        d.d_coop = nullptr;
+        d.coop_cap = 0;
+        TOR_CUDA(ctx, cudaMalloc(&d.d_coop, (size_t)coop_max * sizeof(uint32_t)));
+        d.coop_cap = coop_max;
       }
       tor::BvhRenderParams Q = P;
       Q.spp = pre;
@@ -420,46 +515,39 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       plan.fn<<<grid, block, plan.smem, stream>>>(Q);
       TOR_CUDA(ctx, cudaGetLastError());
       TOR_CUDA(ctx, cudaMemsetAsync(d.d_hist, 0, tor::kCostBuckets * sizeof(uint32_t), stream));
-      TOR_CUDA(ctx, cudaMemsetAsync(d.d_order, 0xff, (size_t)first_wave * sizeof(uint32_t), stream));
+      TOR_CUDA(ctx, cudaMemsetAsync(d.d_order, 0xff, (size_t)warps * 32u * sizeof(uint32_t), stream));
       const int sort_grid = (int)((n + 255) / 256 < (unsigned)(d.sm_count * 8) ? (n + 255) / 256 : d.sm_count * 8);
-      static const uint32_t group = [] {  // developer tuning knob: lanes per cost tier
-        const char* e = getenv("TOR_BVH_DEAL_GROUP");
-        int g = e ? atoi(e) : 8;
-        return (uint32_t)((g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) ? g : 8);
-      }();
-      // Queue order: most expensive class first.  Default: coarse classes with the image order kept inside a class
-      // and warps that take 32 consecutive queue entries at a time (the CHUNKED kernel), so that after the dealt
-      // first wave the lanes of a warp work on neighbouring pixels of the same kind.  TOR_BVH_EXACT_QUEUE=percost
-      // selects the earlier scheme (one class per cost value, arbitrary order inside, one atomic per lane).
-      static const bool coherent = [] {
-        const char* e = getenv("TOR_BVH_EXACT_QUEUE");
-        return !(e && strcmp(e, "percost") == 0);
-      }();
+      const uint32_t group = (uint32_t)tune.deal_group;
+      const uint32_t force = tune.coop_force < 0 ? 0xffffffffu
+                                                 : (uint32_t)(tune.coop_force > 0x7fffffffll ? 0x7fffffffll : tune.coop_force);
       tor::cost_histogram_kernel<<<sort_grid, 256, 0, stream>>>(d.d_cost, n, d.d_hist, coherent ? 1u : 0u);
-      tor::cost_offsets_kernel<<<1, tor::kCostBuckets, 0, stream>>>(d.d_hist);
+      tor::cost_offsets_kernel<<<1, tor::kCostBuckets, 0, stream>>>(d.d_hist, d.d_sched, coherent ? 1u : 0u, lanes,
+                                                                    tune.coop_alpha, coop_max, force);
       if (coherent) {
-        tor::cost_scatter_ordered_kernel<<<8, 1024, 0, stream>>>(d.d_cost, n, d.d_hist, d.d_order, warps, group, n_first,
-                                                              1u);
-        main_plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin, /*chunked=*/true);
+        tor::cost_scatter_ordered_kernel<<<8, 1024, 0, stream>>>(d.d_cost, n, d.d_hist, d.d_order, warps, group, 1u,
+                                                              d.d_sched, d.d_coop);
+        main_plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin, /*chunked=*/true, /*coop=*/coop_max > 0,
+                                 tune.block);
         TOR_CUDA(ctx, cudaFuncSetAttribute(main_plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)main_plan.smem));
         P.chunk = 32;
         P.chunk_guard = 0;
       } else {
         tor::cost_scatter_kernel<<<sort_grid, 256, 0, stream>>>(d.d_cost, n, d.d_hist, d.d_order, warps, group,
-                                                                n_first);
+                                                                d.d_sched, d.d_coop);
       }
       TOR_CUDA(ctx, cudaGetLastError());
       ctx->launches += 4;
       P.order = d.d_order;
-      P.first_wave = first_wave;
-      P.total_slots = (uint32_t)slots;
-    } else if (reorder && sub_log2 == 0 && !getenv("TOR_BVH_NO_SCRAMBLE")) {
+      P.first_wave = warps * 32u;
+      P.sched = d.d_sched;  // sched[0] = 0 when coop_max == 0
+      P.coop_list = d.d_coop;
+    } else if (reorder && sub_log2 == 0 && !tune.no_scramble) {
       // exact mode without cost information (few samples per pixel): scatter the image over the warps so that
       // expensive neighbours do not share one (BvhRenderParams::scramble).  Split-stream units are short, so there
       // the queue stays in image order and the lanes of a warp work on neighbouring pixels.
       P.scramble = coprime_near_golden((uint32_t)total_px);
-    } else if (sub_log2 && getenv("TOR_BVH_FAST_SCRAMBLE")) {  // developer knob: the scattered order in split-stream mode
+    } else if (sub_log2 && tune.fast_scramble) {
       P.scramble = coprime_near_golden((uint32_t)total_px);
     }
     main_plan.fn<<<grid, block, main_plan.smem, stream>>>(P);
@@ -480,6 +568,10 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     TOR_CUDA(ctx, cudaEventRecord(d.ev1, stream));
     d.timed = true;
   }
+  // the per-context scratch (queue heads, cost / order arrays, scene blob) is in use until here, on whatever stream
+  // the caller chose: the next launch, the next scene upload and tor_sync order themselves after this event
+  TOR_CUDA(ctx, cudaEventRecord(d.ev_busy, stream));
+  d.busy = true;
   ctx->launches += 1;
   if (count) ctx->counters_pending = true;
   return TOR_OK;
@@ -512,6 +604,7 @@ int tor_ctx_create(const int* devices, int ndev, tor_ctx** out) {
     }
   }
   tor_ctx* ctx = new tor_ctx();
+  ctx->tune = Tuning::from_env();
   for (int id : ids) {
     DeviceState d;
     d.dev = id;
@@ -531,7 +624,10 @@ int tor_ctx_create(const int* devices, int ndev, tor_ctx** out) {
     d.max_smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     bool ok = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&d.ev0) == cudaSuccess && cudaEventCreate(&d.ev1) == cudaSuccess &&
+              cudaEventCreateWithFlags(&d.ev_busy, cudaEventDisableTiming) == cudaSuccess &&
               cudaMalloc(&d.d_work, 2 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&d.d_sched, 4 * sizeof(uint32_t)) == cudaSuccess &&
+              cudaMemset(d.d_sched, 0, 4 * sizeof(uint32_t)) == cudaSuccess &&
               cudaMalloc(&d.d_hist, tor::kCostBuckets * sizeof(uint32_t)) == cudaSuccess &&
               cudaMalloc(&d.d_counters, 4 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMemset(d.d_counters, 0, 4 * sizeof(unsigned long long)) == cudaSuccess;
@@ -551,7 +647,12 @@ void tor_ctx_destroy(tor_ctx* ctx) {
   for (DeviceState& d : ctx->devs) {
     cudaSetDevice(d.dev);
     if (d.stream) cudaStreamSynchronize(d.stream);
+    if (d.busy && d.ev_busy) cudaEventSynchronize(d.ev_busy);
     if (d.d_blob) cudaFree(d.d_blob);
+    if (d.d_brute) cudaFree(d.d_brute);
+    if (d.d_sched) cudaFree(d.d_sched);
+    if (d.d_coop) cudaFree(d.d_coop);
+    if (d.ev_busy) cudaEventDestroy(d.ev_busy);
     if (d.d_pixels) cudaFree(d.d_pixels);
     if (d.d_work) cudaFree(d.d_work);
     if (d.d_cost) cudaFree(d.d_cost);
@@ -602,6 +703,10 @@ int tor_sync(tor_ctx* ctx) {
   for (DeviceState& d : ctx->devs) {
     TOR_CUDA(ctx, cudaSetDevice(d.dev));
     TOR_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    if (d.busy) {  // also covers renders that tor_render_device_async put on a caller's stream
+      TOR_CUDA(ctx, cudaEventSynchronize(d.ev_busy));
+      d.busy = false;
+    }
   }
   return TOR_OK;
 }
@@ -626,6 +731,14 @@ int tor_render_rows(tor_ctx* ctx, tor_canvas* canvas, const tor_camera* cam, con
   // selected row k (k = 0 .. nsel_total-1) goes to device k mod ndev: cheap sky rows and expensive
   // ground rows interleave across devices.  Seeds use the absolute (row, col), so the image does not
   // depend on ndev (render.nim:59-60).
+  // On an error for device g the devices before it already have kernels and copies into canvas->pixels in flight:
+  // drain them before the caller gets the error and possibly frees the canvas (the original message is kept).
+  auto bail = [&](int code) {
+    std::string msg = ctx->err;
+    tor_sync(ctx);
+    ctx->err = msg;
+    return code;
+  };
   for (int g = 0; g < ndev; ++g) {
     DeviceState& d = ctx->devs[g];
     if (g >= nsel_total) {
@@ -636,16 +749,17 @@ int tor_render_rows(tor_ctx* ctx, tor_canvas* canvas, const tor_camera* cam, con
     const int32_t rs = row_step * ndev;
     const int32_t nsel = (row_end - rb + rs - 1) / rs;
     rc = ensure_capacity(ctx, d, device_blob_bytes(ctx), (size_t)nsel * row_bytes);
-    if (rc) return rc;
+    if (rc) return bail(rc);
     rc = upload_scene_to(ctx, d);
-    if (rc) return rc;
+    if (rc) return bail(rc);
     rc = launch_rows(ctx, d, d.d_pixels, canvas->nrows, ncols, canvas->samples_per_pixel, canvas->gamma_correction,
                      max_depth, flags, rb, row_end, rs, d.stream, /*timed=*/true);
-    if (rc) return rc;
+    if (rc) return bail(rc);
     // device rows are compact; scatter them back to their canvas rows (pitch = rs rows)
     double* dst = canvas->pixels + (size_t)rb * ncols * 3;
-    TOR_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)rs * row_bytes, d.d_pixels, row_bytes, row_bytes, (size_t)nsel,
-                                    cudaMemcpyDeviceToHost, d.stream));
+    cudaError_t ce = cudaMemcpy2DAsync(dst, (size_t)rs * row_bytes, d.d_pixels, row_bytes, row_bytes, (size_t)nsel,
+                                       cudaMemcpyDeviceToHost, d.stream);
+    if (ce != cudaSuccess) return bail(fail(ctx, TOR_ERR_CUDA, std::string("cudaMemcpy2DAsync: ") + cudaGetErrorString(ce)));
   }
   return tor_sync(ctx);
 }
@@ -768,7 +882,7 @@ int tor_get_counters(tor_ctx* ctx, uint64_t out[3]) {
   }
   out[0] = rays;
   out[1] = segs;
-  out[2] = segs * (uint64_t)(ctx->have_scene ? ctx->scene.view.n_objects : 0);
+  out[2] = segs * (uint64_t)(ctx->have_scene ? ctx->objs.size() : 0);
   ctx->trav_counters[0] = boxes;
   ctx->trav_counters[1] = tests;
   ctx->counters_pending = false;
@@ -785,12 +899,30 @@ int tor_get_traversal_counters(tor_ctx* ctx, uint64_t out[2]) {
 int tor_scene_info(tor_ctx* ctx, int64_t out[6]) {
   if (!ctx || !out) return TOR_ERR_INVALID_ARG;
   if (!ctx->have_scene) return fail(ctx, TOR_ERR_INVALID_ARG, "no scene has been set on this context");
-  out[0] = ctx->scene.view.n_objects;
+  out[0] = (int64_t)ctx->objs.size();
   out[1] = ctx->bvh.view.n_nodes;
   out[2] = ctx->bvh.n_leaves;
   out[3] = ctx->bvh.max_depth;
   out[4] = ctx->bvh.view.n_objects - ctx->bvh.view.n_tree_objs;
   out[5] = (int64_t)ctx->bvh.blob.size();
+  return TOR_OK;
+}
+
+int tor_last_schedule(tor_ctx* ctx, int64_t out[4]) {
+  if (!ctx || !out) return TOR_ERR_INVALID_ARG;
+  out[0] = out[1] = out[2] = out[3] = 0;
+  for (DeviceState& d : ctx->devs) {
+    uint32_t h[4] = {0, 0, 0, 0};
+    TOR_CUDA(ctx, cudaSetDevice(d.dev));
+    TOR_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    int rc = wait_idle(ctx, d);
+    if (rc) return rc;
+    TOR_CUDA(ctx, cudaMemcpy(h, d.d_sched, sizeof(h), cudaMemcpyDeviceToHost));
+    out[0] += h[0];
+    out[1] += h[1];
+    out[2] += h[2];
+  }
+  out[3] = (int64_t)ctx->devs.size();
   return TOR_OK;
 }
 

@@ -15,7 +15,16 @@
 //   * objects whose box is not finite (NaN / inf centres, zero-length time interval) are not put in the
 //     tree at all: they sit in an "always" list that every segment tests exactly.
 //
-// Blob layout:  [BvhNode x n_nodes][ObjRec x n_objects (tree leaves first, then the "always" list)]
+// Blob layout:  [BvhNode x n_nodes][cluster boxes][object boxes][ObjRec x n_objects (tree leaves first, then the
+//               "always" list)]
+//
+// The two box tables serve the warp-cooperative search of the render kernel (one warp traces one expensive
+// pixel, tor_kernels_bvh.cuh): tree records are in leaf order, i.e. spatially sorted, so 32 consecutive records
+// form a "cluster".  The warp tests 32 cluster boxes at once, then the 32 object boxes of every cluster the ray
+// enters, and evaluates the surviving objects in parallel lanes.  Both tables hold the same padded, outward
+// rounded float32 boxes as the tree (the same conservativeness argument applies), as structure-of-arrays so that
+// the 32 lanes read consecutive words: cluster boxes float[6][ncl_pad] (lo.x, lo.y, lo.z, hi.x, hi.y, hi.z),
+// object boxes float[6][32] per cluster.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -74,8 +83,10 @@ struct BvhView {  // kernel parameter
   int32_t n_objects;      // records [n_tree_objs, n_objects) are the "always" list
   int32_t has_movers;
   uint32_t off_nodes, off_objs;
-  uint32_t nodes_bytes;   // blob prefix holding the nodes
+  uint32_t hot_bytes;     // blob prefix holding the nodes and the two box tables
   uint32_t total_bytes;
+  uint32_t off_cboxes, off_oboxes;  // cluster boxes float[6][ncl_pad]; object boxes float[n_clusters][6][32]
+  int32_t n_clusters, ncl_pad;      // clusters of 32 consecutive tree records; ncl_pad = n_clusters rounded up to 32
   float s_limit;          // ray origins with a larger |coordinate| take the "test everything" route
   int32_t max_depth;
 };
@@ -98,6 +109,7 @@ static inline int bvh_max_leaf() {
 }
 #define kBvhMaxLeaf (::tor::bvh_max_leaf())
 static constexpr int kBvhStackDepth = 40;  // >= max tree depth (forced median splits below bound it)
+static constexpr int kBvhMaxObjects = 1 << 24;  // leaf references hold first_record << 4 in 31 bits; depth <= 16 + 22
 
 namespace bvh_detail {
 
@@ -221,7 +233,7 @@ struct Builder {
       return mid;
     };
     if (!(ext > 0.0)) return n <= kBvhMaxLeaf ? -1 : median(axis);  // coincident centroids
-    if (depth >= 16) return n <= kBvhMaxLeaf ? -1 : median(axis);   // bounds the depth: <= 16 + log2(65536/leaf)
+    if (depth >= 16) return n <= kBvhMaxLeaf ? -1 : median(axis);   // bounds the depth: <= 16 + log2(2^24/leaf)
 
     // binned surface-area heuristic on every axis
     constexpr int kBins = 16;
@@ -386,8 +398,8 @@ static inline bool pack_bvh(const std::vector<tor_hittable>& objs, const tor_cam
                             std::string* err) {
   using namespace bvh_detail;
   const int n = (int)objs.size();
-  if (n <= 0 || n > 65535) {
-    *err = "object count must be in 1..65535";
+  if (n <= 0 || n > kBvhMaxObjects) {
+    *err = "object count must be in 1..16777216";
     return false;
   }
   double time_lo = 0.0, time_hi = 0.0;  // rays.nim:19 — scattered Metal / Dielectric rays carry time 0.0
@@ -399,6 +411,7 @@ static inline bool pack_bvh(const std::vector<tor_hittable>& objs, const tor_cam
 
   std::vector<Prim> prims;
   std::vector<int> always;
+  std::vector<Box> obj_box((size_t)n);  // by original index (tree objects only)
   double S = 0.0;  // largest |coordinate| of any box or of the camera (ray origins live on the objects or the lens)
   for (int k = 0; k < 3; ++k) {
     double lens = fabs(cam.lens_radius) * (fabs(cam.u[k]) + fabs(cam.v[k]));
@@ -444,6 +457,7 @@ static inline bool pack_bvh(const std::vector<tor_hittable>& objs, const tor_cam
       p.c[k] = 0.5 * (p.b.lo[k] + p.b.hi[k]);
       S = std::max(S, std::max(fabs(p.b.lo[k]), fabs(p.b.hi[k])));
     }
+    obj_box[(size_t)i] = p.b;
     prims.push_back(p);
   }
 
@@ -517,19 +531,54 @@ static inline bool pack_bvh(const std::vector<tor_hittable>& objs, const tor_cam
     r.orig = (uint32_t)order[(size_t)j];
   }
 
+  // box tables of the warp-cooperative search: clusters of 32 consecutive tree records
+  const int n_clusters = (n_tree + 31) / 32;
+  const int ncl_pad = std::max(32, (n_clusters + 31) / 32 * 32);
+  std::vector<float> cboxes((size_t)6 * ncl_pad), oboxes((size_t)n_clusters * 6 * 32);
+  for (int c = 0; c < ncl_pad; ++c) {
+    float lo[3], hi[3];
+    Builder::store_empty(lo, hi);
+    if (c < n_clusters) {
+      Box cb;
+      box_reset(cb);
+      for (int j = 32 * c; j < std::min(n_tree, 32 * c + 32); ++j) box_grow(cb, obj_box[(size_t)order[(size_t)j]]);
+      B.store_box(lo, hi, cb);
+      for (int i = 0; i < 32; ++i) {
+        float olo[3], ohi[3];
+        Builder::store_empty(olo, ohi);
+        const int j = 32 * c + i;
+        if (j < n_tree) B.store_box(olo, ohi, obj_box[(size_t)order[(size_t)j]]);
+        for (int k = 0; k < 3; ++k) {
+          oboxes[((size_t)c * 6 + k) * 32 + i] = olo[k];
+          oboxes[((size_t)c * 6 + 3 + k) * 32 + i] = ohi[k];
+        }
+      }
+    }
+    for (int k = 0; k < 3; ++k) {
+      cboxes[(size_t)k * ncl_pad + c] = lo[k];
+      cboxes[(size_t)(3 + k) * ncl_pad + c] = hi[k];
+    }
+  }
+
   BvhView& v = out->view;
   v.n_nodes = (int32_t)nodes.size();
   v.n_tree_objs = n_tree;
   v.n_objects = n;
   v.has_movers = has_movers ? 1 : 0;
   v.off_nodes = 0;
-  v.nodes_bytes = (uint32_t)(nodes.size() * sizeof(BvhNode));
-  v.off_objs = v.nodes_bytes;
+  v.off_cboxes = (uint32_t)(nodes.size() * sizeof(BvhNode));
+  v.off_oboxes = v.off_cboxes + (uint32_t)(cboxes.size() * sizeof(float));
+  v.hot_bytes = v.off_oboxes + (uint32_t)(oboxes.size() * sizeof(float));
+  v.n_clusters = n_clusters;
+  v.ncl_pad = ncl_pad;
+  v.off_objs = v.hot_bytes;
   v.total_bytes = v.off_objs + (uint32_t)(recs.size() * sizeof(ObjRec));
   v.s_limit = bvh_detail::f32_down(1.001 * S);  // the padding was sized for origins within S (see header)
   v.max_depth = B.max_depth;
-  out->blob.resize(v.total_bytes);  // nodes + records cover every byte
-  memcpy(out->blob.data() + v.off_nodes, nodes.data(), v.nodes_bytes);
+  out->blob.resize(v.total_bytes);  // nodes + box tables + records cover every byte
+  memcpy(out->blob.data() + v.off_nodes, nodes.data(), nodes.size() * sizeof(BvhNode));
+  memcpy(out->blob.data() + v.off_cboxes, cboxes.data(), cboxes.size() * sizeof(float));
+  if (!oboxes.empty()) memcpy(out->blob.data() + v.off_oboxes, oboxes.data(), oboxes.size() * sizeof(float));
   memcpy(out->blob.data() + v.off_objs, recs.data(), recs.size() * sizeof(ObjRec));
   out->max_depth = B.max_depth;
   out->n_leaves = B.n_leaves;

@@ -51,12 +51,20 @@ struct BvhRenderParams {
   // of a warp get pixels from all over the image, so the few expensive pixels of a latency-bound render end up in
   // different warps and each runs in a nearly idle warp once its cheap neighbours are done.
   uint32_t scramble;
-  // order != NULL and first_wave != 0: the first first_wave entries of `order` are not queued but dealt: the lane
-  // with global index g starts on order[g] (0xffffffff = nothing).  The queue then serves order[first_wave ..
-  // total_slots).  The host deals the most expensive pixels so that every warp starts with the same mix of costs
-  // (cost_scatter_kernel).
+  // order != NULL and first_wave != 0: the head of `order` is not queued but dealt, 32 entries per warp: lane l of
+  // the warp with dealing rank w starts on order[32 * w + l] (0xffffffff = nothing), and the queue serves what
+  // follows.  The host deals the most expensive pixels so that every warp starts with the same mix of costs
+  // (cost_scatter_ordered_kernel).  first_wave = 32 * (warps of the grid): the dealt region when no warp is
+  // cooperative; with n_coop cooperative warps (below) the region is 32 * (warps - n_coop) entries and the queue
+  // starts right behind it.  Both the scatter kernels and this kernel derive the layout from sched[0].
   uint32_t first_wave;
-  uint32_t total_slots;
+  // Warp-cooperative pixels (exact mode, COOP kernels).  sched[0] = n_coop, computed on the device from the cost
+  // histogram (cost_offsets_kernel): the n_coop most expensive pixels are not given to single lanes; pixel
+  // coop_list[r] is traced by the whole warp with rank r (rank = warp-in-CTA * gridDim.x + blockIdx.x, which spreads
+  // them over all SMs), whose lanes share the closest-hit search of every bounce segment.  Those warps join the
+  // ordinary queue afterwards.  NULL = no cooperative pixels.
+  const uint32_t* sched;
+  const uint32_t* coop_list;
   // Lanes of each warp that take pixels (1..32; 32 unless the TOR_BVH_LANES tuning knob says otherwise).
   int32_t lanes_per_warp;
   // Split-stream mode (TOR_MODE_FAST, include/tor_b200.h): every pixel's sample loop is cut into 2^sub_log2
@@ -99,6 +107,16 @@ __device__ __forceinline__ int4 ld16i(const void* generic_base, uint32_t shared_
   return reinterpret_cast<const int4*>(generic_base)[idx16];
 }
 
+template <bool SHARED>
+__device__ __forceinline__ float ld4f(const void* generic_base, uint32_t shared_base, int32_t idx4) {
+  if (SHARED) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(shared_base + 4u * (uint32_t)idx4));
+    return v;
+  }
+  return reinterpret_cast<const float*>(generic_base)[idx4];
+}
+
 struct QCache {  // lerp parameter of moving_spheres.nim:41-42, one divide per (time0, time1) per segment
   double t0, t1, q;
 };
@@ -126,14 +144,14 @@ __device__ __forceinline__ V3 rec_center(const double2* __restrict__ r, uint32_t
   return c0;
 }
 
-template <int BLOCK, int STAGE, bool CHUNKED>
+template <int BLOCK, int STAGE, bool CHUNKED, bool COOP>
 __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_bvh_kernel(const __grid_constant__ BvhRenderParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t stage_bar;
 
   const int tid = threadIdx.x;
   const BvhView& bv = P.bv;
-  const uint32_t staged_bytes = STAGE == 2 ? bv.total_bytes : (STAGE == 1 ? bv.nodes_bytes : 0u);
+  const uint32_t staged_bytes = STAGE == 2 ? bv.total_bytes : (STAGE == 1 ? bv.hot_bytes : 0u);
 
   if (tid == 0) {
     mbar_init(&stage_bar, 1);
@@ -154,6 +172,11 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   const float4* __restrict__ nodes = reinterpret_cast<const float4*>((STAGE >= 1 ? smem : P.blob) + bv.off_nodes);
   const double2* __restrict__ recs = reinterpret_cast<const double2*>((STAGE == 2 ? smem : P.blob) + bv.off_objs);
   const uint32_t nodes_sa = smem_u32(smem) + bv.off_nodes;  // meaningful for STAGE >= 1 only
+  // box tables of the warp-cooperative search (COOP kernels only)
+  const float* __restrict__ cboxes = reinterpret_cast<const float*>((STAGE >= 1 ? smem : P.blob) + bv.off_cboxes);
+  const float* __restrict__ oboxes = reinterpret_cast<const float*>((STAGE >= 1 ? smem : P.blob) + bv.off_oboxes);
+  const uint32_t cboxes_sa = smem_u32(smem) + bv.off_cboxes, oboxes_sa = smem_u32(smem) + bv.off_oboxes;
+  __shared__ uint32_t coop_cand[COOP ? BLOCK / 32 : 1][32];  // candidate records of each cooperative warp
 
   __shared__ unsigned long long warp_chunk[CHUNKED ? BLOCK / 32 : 1][2];  // [next, end) slots of each warp's chunk
   unsigned long long* const wchunk = warp_chunk[CHUNKED ? tid >> 5 : 0];
@@ -164,8 +187,16 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   const double t_min = 0.001;  // render.nim:28
   const unsigned long long total_px = (unsigned long long)P.nsel_rows * (unsigned long long)P.ncols;
   const unsigned long long total_units = total_px << P.sub_log2;
+  // Layout of the cost-ranked order (see BvhRenderParams): [dealt: 32 per non-cooperative warp][queue]
+  const uint32_t n_coop = (COOP && P.sched) ? P.sched[0] : 0u;  // cooperative pixels
+  const uint32_t grid_warps = gridDim.x * (uint32_t)(BLOCK / 32);
+  const uint32_t coop_warps = n_coop < grid_warps ? n_coop : grid_warps;  // warps that start cooperatively
+  const uint32_t wrank = (uint32_t)(tid >> 5) * gridDim.x + blockIdx.x;   // this warp's rank; < coop_warps: cooperative
+  const uint32_t first_wave = P.first_wave ? (grid_warps - coop_warps) * 32u : 0u;
+  const uint32_t n_ranked = (uint32_t)total_px - n_coop;  // pixels that go to single lanes
   // length of the shared queue: everything, or what the cost-ranked order leaves after the dealt first wave
-  const unsigned long long queue_len = P.order ? (unsigned long long)(P.total_slots - P.first_wave) : total_units;
+  const unsigned long long queue_len =
+      P.order ? (unsigned long long)(n_ranked - (n_ranked < first_wave ? n_ranked : first_wave)) : total_units;
   const int refill = P.refill;
 
   Lane L;
@@ -215,15 +246,20 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
       //   x2 <= t_min*a*(1 - 2^-40)  =>  both roots round to <= t_min: no root in (t_min, inf)   [the sphere the
       //                                   ray starts on, spheres behind the origin]
       //   x1 >= best_t*a*(1 + 2^-40) =>  the first root is valid and strictly beyond the closest so far
+      //   x1 <= t_min*a*(1 - 2^-40)  =>  the first root rounds to <= t_min: go straight to the second
       const bool a_ok = a >= 1e-200 && a <= 1e200;
       const double ta = t_min * a;
       const double ba = best_t * a;
-      const bool none = a_ok && x2 <= ta * (1.0 - 0x1p-40);
+      const double ta_lo = ta * (1.0 - 0x1p-40);
+      const bool none = a_ok && x2 <= ta_lo;
       const bool behind = a_ok && x1 >= ba * (1.0 + 0x1p-40);
       if (!none && !behind) {
         double t = INF;
-        double sol = x1 / a;
-        if (t_min < sol) {
+        // x1 <= t_min*a*(1 - 2^-40) => x1 / a rounds to <= t_min: the first root fails `t_min < sol` and only the
+        // second divide is needed (a ray that starts on this sphere and crosses it: every glass-internal segment)
+        const bool skip1 = a_ok && x1 <= ta_lo;
+        double sol = skip1 ? 0.0 : x1 / a;
+        if (!skip1 && t_min < sol) {
           t = sol;
         } else {
           sol = x2 / a;
@@ -237,6 +273,49 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
         }
       }
     }
+  };
+
+  // A new bounce segment: resets the closest hit and derives the float32 ray of the slab tests.  Components of d far
+  // below the largest one are replaced by +-2^-60 * dmax (a direction change below 2^-60, negligible against the box
+  // padding) so that 1/d stays finite; rays outside the range the padding was derived for test everything instead.
+  auto ray_setup = [&]() {
+    best_t = INF;
+    best_orig = 0xffffffffu;
+    best_rec = -1;
+    best_f = __int_as_float(0x7f800000);
+    qc.t0 = qc.t1 = __longlong_as_double(0x7ff8000000000000ll);  // NaN: never equal, forces the first divide
+    const V3 o = L.o, d = L.d;
+    a = len2(d);
+    float dxf = __double2float_rn(d.x), dyf = __double2float_rn(d.y), dzf = __double2float_rn(d.z);
+    float oxf = __double2float_rn(o.x), oyf = __double2float_rn(o.y), ozf = __double2float_rn(o.z);
+    float dmax = fmaxf(fabsf(dxf), fmaxf(fabsf(dyf), fabsf(dzf)));
+    float omax = fmaxf(fabsf(oxf), fmaxf(fabsf(oyf), fabsf(ozf)));
+    bool ok = dmax >= 0x1p-40f && dmax <= 0x1p40f && omax <= bv.s_limit;
+    ok = ok && dxf == dxf && dyf == dyf && dzf == dzf && oxf == oxf && oyf == oyf && ozf == ozf;
+    if (ok) {
+      float dmin = dmax * 0x1p-60f;
+      if (fabsf(dxf) < dmin) dxf = copysignf(dmin, dxf);
+      if (fabsf(dyf) < dmin) dyf = copysignf(dmin, dyf);
+      if (fabsf(dzf) < dmin) dzf = copysignf(dmin, dzf);
+      idx = __frcp_rn(dxf);
+      idy = __frcp_rn(dyf);
+      idz = __frcp_rn(dzf);
+      oix = oxf * idx;
+      oiy = oyf * idy;
+      oiz = ozf * idz;
+    } else {
+      idx = idy = idz = 0.f;  // every slab interval becomes [0, 0]: all boxes pass
+      oix = oiy = oiz = 0.f;
+    }
+  };
+  // The slab test of the traversal loop on one box (the same expression, so the same conservativeness argument).
+  auto slab_hit = [&](float lx, float ly, float lz, float hx, float hy, float hz) -> bool {
+    const float ax0 = fmaf(lx, idx, -oix), ax1 = fmaf(hx, idx, -oix);
+    const float ay0 = fmaf(ly, idy, -oiy), ay1 = fmaf(hy, idy, -oiy);
+    const float az0 = fmaf(lz, idz, -oiz), az1 = fmaf(hz, idz, -oiz);
+    const float nr = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.f));
+    const float fr = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), best_f));
+    return nr <= fr;
   };
 
   // queue slot -> work unit when there is no cost-ranked order: consecutive slots are the sample ranges of one pixel;
@@ -268,6 +347,129 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
     out[0] = out[1] = out[2] = 0.0;
     return false;
   };
+
+  // ================================================================= warp-cooperative pixels
+  // A pixel's samples are one serial chain (render.nim:59-67), so the render cannot end before its most expensive
+  // pixel does, and a single lane needs microseconds per bounce segment.  The n_coop most expensive pixels of the
+  // cost pre-pass are therefore traced by a whole warp each: every lane carries the same path state (same RNG
+  // stream, same arithmetic, hence the same bits — nothing is broadcast), and the lanes share the only part of a
+  // segment that has parallelism, the closest-hit search:
+  //   1. 32 cluster boxes per step (a cluster = 32 consecutive tree records), float32 slab test;
+  //   2. the 32 object boxes of every cluster the ray enters; survivors are appended to a candidate list;
+  //   3. one candidate per lane through the reference's float64 sphere test (test_rec), all at once;
+  //   4. argmin over the lanes of (t, original index) — the order-free form of hittables_lists.nim:48-55 — with
+  //      three warp reductions on the bit pattern of t (monotonic: t_min < t <= +inf).
+  // Shading then runs on all lanes redundantly (converged, one pass).  The set of objects tested is a superset of
+  // the objects with a root (same padded boxes as the tree), so the hit is the lane mode's, bit for bit.
+  if constexpr (COOP) {
+    if (wrank < coop_warps) {  // warp-uniform
+      const int lane = tid & 31;
+      const unsigned lt_mask = (1u << lane) - 1u;
+      uint32_t* const cand = coop_cand[tid >> 5];
+      uint32_t ncand = 0;  // warp-uniform
+      // all listed candidates through the exact test, one per lane
+      auto flush = [&]() {
+        __syncwarp();
+        if ((uint32_t)lane < ncand) test_rec((int32_t)cand[lane]);
+        __syncwarp();
+        if (lane == 0) test_count += ncand;
+        ncand = 0;
+      };
+      // every lane with `has` appends `val`; the list never holds more than 32 entries
+      auto push = [&](bool has, uint32_t val) {
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        const uint32_t cnt = (uint32_t)__popc(m);
+        if (ncand + cnt > 32u) flush();
+        if (has) cand[ncand + (uint32_t)__popc(m & lt_mask)] = val;
+        ncand += cnt;
+      };
+      // one pixel per warp in a real render (n_coop <= warps); more only when a test forces it
+      for (uint32_t cr = wrank; cr < n_coop; cr += grid_warps) {
+      pid = P.coop_list[cr];
+      {
+        const int32_t ri = (int32_t)(pid / (uint32_t)P.ncols);
+        L.col = (int32_t)(pid - (uint32_t)ri * (uint32_t)P.ncols);
+        L.row = P.row_begin + ri * P.row_step;
+      }
+      rng_seed_pixel(L.rng, L.row, L.col, 0);  // render.nim:59-60
+      L.pix = v3(0, 0, 0);
+      for (int32_t s = 0; s < P.spp; ++s) {  // render.nim:62
+        start_sample(L, P.cam, P.nrows, P.ncols);
+        if (lane == 0) ++ray_count;
+        V3 color = v3(0, 0, 0);
+        for (;;) {  // render.nim:25-47, one bounce segment per pass
+          if (lane == 0) ++seg_count;
+          ray_setup();
+          for (int32_t base = bv.n_tree_objs; base < bv.n_objects; base += 32)  // objects without a finite box
+            push(base + lane < bv.n_objects, (uint32_t)(base + lane));
+          for (int32_t cb = 0; cb < bv.n_clusters; cb += 32) {
+            const int32_t c = cb + lane;
+            bool h = false;
+            if (c < bv.n_clusters)
+              h = slab_hit(ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, c), ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, bv.ncl_pad + c),
+                           ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 2 * bv.ncl_pad + c),
+                           ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 3 * bv.ncl_pad + c),
+                           ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 4 * bv.ncl_pad + c),
+                           ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 5 * bv.ncl_pad + c));
+            unsigned hit_clusters = __ballot_sync(0xffffffffu, h);
+            if (lane == 0) ++box_count;
+            while (hit_clusters) {
+              const int32_t ci = cb + __ffs(hit_clusters) - 1;
+              hit_clusters &= hit_clusters - 1u;
+              const int32_t obj = ci * 32 + lane;
+              const int32_t ob = ci * 192 + lane;
+              bool ho = false;
+              if (obj < bv.n_tree_objs)
+                ho = slab_hit(ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 32),
+                              ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 64), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 96),
+                              ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 128), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 160));
+              if (lane == 0) ++box_count;
+              push(ho, (uint32_t)obj);
+            }
+          }
+          flush();
+          // closest hit of the warp: lexicographic minimum of (t, original index)
+          {
+            const unsigned long long tb = (unsigned long long)__double_as_longlong(best_t);
+            const uint32_t hi = (uint32_t)(tb >> 32), lo = (uint32_t)tb;
+            const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+            const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+            const bool is_min = hi == mhi && lo == mlo;
+            const uint32_t morig = __reduce_min_sync(0xffffffffu, is_min ? best_orig : 0xffffffffu);
+            const unsigned win = __ballot_sync(0xffffffffu, is_min && best_orig == morig);
+            best_rec = __shfl_sync(0xffffffffu, best_rec, __ffs(win) - 1);
+            best_t = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | (unsigned long long)mlo));
+          }
+          if (best_rec < 0) {
+            color = shade_miss(L);
+            break;
+          }
+          const double2* __restrict__ r = recs + kRecStride16 * best_rec;
+          const double2 a2 = r[2], a6 = r[6], a7 = r[7];
+          const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
+          Surface S;
+          S.center = rec_center(r, kind_mat, L.time, qc);  // moving_spheres.nim:61
+          S.inv_r = a2.y;
+          S.albedo = v3(a6.x, a6.y, a7.x);
+          S.fuzz_or_ior = a7.y;
+          S.mat_kind = (kind_mat >> 8) & 0xffu;
+          if (shade_hit(L, best_t, S, P.max_depth)) break;  // absorbed or depth exhausted: black
+        }
+        L.pix.x += color.x;  // render.nim:67
+        L.pix.y += color.y;
+        L.pix.z += color.z;
+      }
+      if (lane == 0) {
+        double* out = P.pixels + 3ull * pid;  // the sum; draw_kernel applies canvas.nim:47-54 afterwards
+        out[0] = L.pix.x;
+        out[1] = L.pix.y;
+        out[2] = L.pix.z;
+      }
+      __syncwarp();
+      }
+      first_fetch = false;  // cooperative warps were dealt nothing; they join the queue now
+    }
+  }
 
   for (;;) {
     // =================================================================== phase S
@@ -325,13 +527,13 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
         for (;;) {
           if (first_fetch) {  // dealt pixel of this lane, if any
             first_fetch = false;
-            const uint32_t gid = blockIdx.x * BLOCK + tid;
-            pid = gid < P.first_wave ? P.order[gid] : 0xffffffffu;
+            const uint32_t gid = (wrank - coop_warps) * 32u + (uint32_t)(tid & 31);
+            pid = (wrank >= coop_warps && gid < first_wave) ? P.order[gid] : 0xffffffffu;
             if (pid == 0xffffffffu) continue;
           } else if (P.first_wave) {
-            const unsigned long long slot = P.first_wave + atomicAdd(P.work_counter, 1ull);
-            if (slot >= P.total_slots) break;
-            pid = P.order[slot];
+            const unsigned long long slot = atomicAdd(P.work_counter, 1ull);
+            if (slot >= queue_len) break;
+            pid = P.order[first_wave + slot];
           } else {
             const unsigned long long slot = atomicAdd(P.work_counter, 1ull);
             if (slot >= total_units) break;
@@ -347,8 +549,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
       // the same few materials.  Warp-uniform loop: each pass hands one slot to every lane that still needs one.
       if (first_fetch) {  // cost-ranked order: the pixel dealt to this lane, if any
         first_fetch = false;
-        const uint32_t gid = blockIdx.x * BLOCK + tid;
-        pid = need_pixel && gid < P.first_wave ? P.order[gid] : 0xffffffffu;
+        const uint32_t gid = (wrank - coop_warps) * 32u + (uint32_t)(tid & 31);
+        pid = (need_pixel && wrank >= coop_warps && gid < first_wave) ? P.order[gid] : 0xffffffffu;
         if (pid != 0xffffffffu) need_pixel = !begin_unit();
       }
       for (;;) {
@@ -383,7 +585,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
             active = false;
           } else if (rank < take) {
             const unsigned long long slot = base + (unsigned long long)rank;
-            pid = P.order ? P.order[P.first_wave + slot] : unit_of_slot(slot);
+            pid = P.order ? P.order[first_wave + slot] : unit_of_slot(slot);
             need_pixel = !begin_unit();  // an empty sample range (spp < ranges): take another slot in the next pass
           }
         }
@@ -400,40 +602,10 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
     __syncwarp();
     if (active && need_setup) {
       need_setup = false;
-      best_t = INF;
-      best_orig = 0xffffffffu;
-      best_rec = -1;
-      best_f = __int_as_float(0x7f800000);
-      qc.t0 = qc.t1 = __longlong_as_double(0x7ff8000000000000ll);  // NaN: never equal, forces the first divide
       if (P.max_depth <= 0) {
         trav_done = true;
       } else {
-        const V3 o = L.o, d = L.d;
-        a = len2(d);
-        // float32 ray for the slab tests.  Components of d far below the largest one are replaced by
-        // +-2^-60 * dmax (a direction change below 2^-60, negligible against the box padding) so that 1/d
-        // stays finite; rays outside the range the padding was derived for test everything instead.
-        float dxf = __double2float_rn(d.x), dyf = __double2float_rn(d.y), dzf = __double2float_rn(d.z);
-        float oxf = __double2float_rn(o.x), oyf = __double2float_rn(o.y), ozf = __double2float_rn(o.z);
-        float dmax = fmaxf(fabsf(dxf), fmaxf(fabsf(dyf), fabsf(dzf)));
-        float omax = fmaxf(fabsf(oxf), fmaxf(fabsf(oyf), fabsf(ozf)));
-        bool ok = dmax >= 0x1p-40f && dmax <= 0x1p40f && omax <= bv.s_limit;
-        ok = ok && dxf == dxf && dyf == dyf && dzf == dzf && oxf == oxf && oyf == oyf && ozf == ozf;
-        if (ok) {
-          float dmin = dmax * 0x1p-60f;
-          if (fabsf(dxf) < dmin) dxf = copysignf(dmin, dxf);
-          if (fabsf(dyf) < dmin) dyf = copysignf(dmin, dyf);
-          if (fabsf(dzf) < dmin) dzf = copysignf(dmin, dzf);
-          idx = __frcp_rn(dxf);
-          idy = __frcp_rn(dyf);
-          idz = __frcp_rn(dzf);
-          oix = oxf * idx;
-          oiy = oyf * idy;
-          oiz = ozf * idz;
-        } else {
-          idx = idy = idz = 0.f;  // every slab interval becomes [0, 0]: all boxes pass
-          oix = oiy = oiz = 0.f;
-        }
+        ray_setup();
         for (int32_t ri = bv.n_tree_objs; ri < bv.n_objects; ++ri) {  // objects without a finite box
           test_rec(ri);
           ++test_count;
@@ -569,43 +741,104 @@ __global__ void __launch_bounds__(256) cost_histogram_kernel(const uint32_t* __r
     if (h[i]) atomicAdd(&hist[i], h[i]);
 }
 
-// hist[b] := number of pixels in buckets above b (queue offset of bucket b, most expensive bucket first)
-__global__ void __launch_bounds__(kCostBuckets) cost_offsets_kernel(uint32_t* __restrict__ hist) {
+// Lower bound of the costs that fall into a class (inverse of cost_class).
+__device__ __forceinline__ uint32_t class_floor(uint32_t cls, uint32_t coarse) {
+  if (!coarse) return cls;
+  return cls < 16u ? cls << 2 : 64u + ((cls - 16u) << 3);
+}
+
+// hist[b] := number of pixels in buckets above b (queue offset of bucket b, most expensive bucket first).
+// Also decides how many of the most expensive pixels are traced warp-cooperatively (sched[0] = n_coop): a pixel
+// qualifies when its pre-pass cost exceeds coop_alpha times the mean cost per lane of this launch — such a pixel
+// could not finish within the time the bulk of the image takes even if its lane started at once — and at most
+// coop_max pixels qualify (one per cooperative warp).  coop_max == 0 switches the mechanism off.
+__global__ void __launch_bounds__(kCostBuckets) cost_offsets_kernel(uint32_t* __restrict__ hist, uint32_t* __restrict__ sched,
+                                                                    uint32_t coarse, unsigned long long lanes,
+                                                                    float coop_alpha, uint32_t coop_max,
+                                                                    uint32_t coop_force) {
   __shared__ uint32_t s[kCostBuckets];
+  __shared__ unsigned long long total_cost;
+  __shared__ uint32_t n_above;
   const int t = threadIdx.x;            // t = 0 is the most expensive bucket
   const int b = kCostBuckets - 1 - t;
-  s[t] = hist[b];
+  const uint32_t count = hist[b];
+  if (t == 0) {
+    total_cost = 0ull;
+    n_above = 0u;
+  }
+  s[t] = count;
   __syncthreads();
+  if (count) atomicAdd(&total_cost, (unsigned long long)count * (unsigned long long)(class_floor((uint32_t)b, coarse) + (coarse ? 2u : 0u)));
   for (int ofs = 1; ofs < kCostBuckets; ofs <<= 1) {  // inclusive scan
     uint32_t v = t >= ofs ? s[t - ofs] : 0u;
     __syncthreads();
     s[t] += v;
     __syncthreads();
   }
-  hist[b] = s[t] - hist[b];  // exclusive
+  hist[b] = s[t] - count;  // exclusive
+  if (sched) {
+    // mean cost per lane, in the pre-pass's units
+    const float per_lane = (float)total_cost / (float)(lanes ? lanes : 1ull);
+    if (count && (float)class_floor((uint32_t)b, coarse) > coop_alpha * per_lane) atomicAdd(&n_above, count);
+    __syncthreads();
+    if (t == 0) {
+      uint32_t k = n_above < coop_max ? n_above : coop_max;
+      if (coop_force != 0xffffffffu) k = coop_force < coop_max ? coop_force : coop_max;  // developer / test override
+      const uint32_t n = s[kCostBuckets - 1];                                            // all pixels
+      sched[0] = k < n ? k : n;
+      sched[1] = n_above;
+      sched[2] = (uint32_t)(total_cost > 0xffffffffull ? 0xffffffffull : total_cost);
+    }
+  }
 }
 
-// pos = rank of the pixel, most expensive first.  The first n_first ranks are dealt to the lanes like cards, in tiers
-// of `group` lanes: ranks 0 .. warps*group-1 go to lanes 0..group-1 of the warps (rank q -> warp q mod warps), the next
-// warps*group ranks to lanes group..2*group-1, and so on.  Every warp starts with the same mix of costs, equally
-// expensive pixels sit in neighbouring lanes of the same tier, and the ranks after the first wave are queued in order.
+// pos = rank of the pixel, most expensive first.  Ranks below n_coop = sched[0] go to the cooperative warps
+// (coop_list[pos]).  The next ranks are dealt to the remaining warps' lanes like cards, in tiers of `group` lanes:
+// ranks 0 .. warps*group-1 go to lanes 0..group-1 of the warps (rank q -> warp q mod warps), the next warps*group ranks
+// to lanes group..2*group-1, and so on.  Every warp starts with the same mix of costs, equally expensive pixels sit
+// in neighbouring lanes of the same tier, and the ranks after the first wave are queued in order.
+// warps_all = warps of the render grid (0: no dealing, everything is queued).
+struct RankLayout {
+  uint32_t n_coop, warps, first_wave, tier, n_first;
+};
+__device__ __forceinline__ RankLayout rank_layout(const uint32_t* __restrict__ sched, uint32_t n, uint32_t warps_all,
+                                                  uint32_t group) {
+  RankLayout r;
+  r.n_coop = sched ? sched[0] : 0u;
+  r.warps = warps_all ? warps_all - (r.n_coop < warps_all ? r.n_coop : warps_all) : 0u;  // warps that are dealt pixels
+  r.first_wave = r.warps * 32u;
+  r.tier = r.warps * group;
+  const uint32_t n_ranked = n - r.n_coop;
+  r.n_first = n_ranked < r.first_wave ? n_ranked : r.first_wave;
+  return r;
+}
+__device__ __forceinline__ void place_rank(const RankLayout& r, uint32_t pos, uint32_t pixel, uint32_t group,
+                                           uint32_t* __restrict__ order, uint32_t* __restrict__ coop_list) {
+  if (pos < r.n_coop) {
+    coop_list[pos] = pixel;
+    return;
+  }
+  pos -= r.n_coop;
+  uint32_t slot;
+  if (pos < r.n_first) {
+    const uint32_t t = pos / r.tier, q = pos - t * r.tier;
+    slot = (q % r.warps) * 32u + t * group + q / r.warps;
+  } else {
+    slot = r.first_wave + (pos - r.n_first);
+  }
+  order[slot] = pixel;
+}
+
 __global__ void __launch_bounds__(256) cost_scatter_kernel(const uint32_t* __restrict__ cost, uint32_t n,
                                                            uint32_t* __restrict__ offsets, uint32_t* __restrict__ order,
-                                                           uint32_t warps, uint32_t group, uint32_t n_first) {
-  const uint32_t first_wave = warps * 32u, tier = warps * group;
+                                                           uint32_t warps_all, uint32_t group,
+                                                           const uint32_t* __restrict__ sched,
+                                                           uint32_t* __restrict__ coop_list) {
+  const RankLayout r = rank_layout(sched, n, warps_all, group);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint32_t c = cost[i];
     uint32_t pos = atomicAdd(&offsets[c < kCostBuckets ? c : kCostBuckets - 1], 1u);
-    uint32_t slot;
-    if (warps == 0) {
-      slot = pos;
-    } else if (pos < n_first) {
-      const uint32_t t = pos / tier, q = pos - t * tier;
-      slot = (q % warps) * 32u + t * group + q / warps;
-    } else {
-      slot = first_wave + (pos - n_first);
-    }
-    order[slot] = i;
+    place_rank(r, pos, i, group, order, coop_list);
   }
 }
 
@@ -638,9 +871,11 @@ __global__ void __launch_bounds__(256) substream_reduce_kernel(const double* __r
 // step).  Lanes of a warp with the same class take consecutive ranks with one atomic (warp-aggregated).
 __global__ void __launch_bounds__(1024) cost_scatter_ordered_kernel(const uint32_t* __restrict__ cost, uint32_t n,
                                                                     uint32_t* __restrict__ offsets,
-                                                                    uint32_t* __restrict__ order, uint32_t warps,
-                                                                    uint32_t group, uint32_t n_first, uint32_t coarse) {
-  const uint32_t first_wave = warps * 32u, tier = warps * group;
+                                                                    uint32_t* __restrict__ order, uint32_t warps_all,
+                                                                    uint32_t group, uint32_t coarse,
+                                                                    const uint32_t* __restrict__ sched,
+                                                                    uint32_t* __restrict__ coop_list) {
+  const RankLayout r = rank_layout(sched, n, warps_all, group);
   const uint32_t lane = threadIdx.x & 31u;
   for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
     const uint32_t i = i0 + threadIdx.x;
@@ -651,17 +886,7 @@ __global__ void __launch_bounds__(1024) cost_scatter_ordered_kernel(const uint32
     uint32_t base = 0;
     if (in && lane == leader) base = atomicAdd(&offsets[cls], (uint32_t)__popc(peers));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (in) {
-      const uint32_t pos = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-      uint32_t slot;
-      if (pos < n_first) {
-        const uint32_t t = pos / tier, q = pos - t * tier;
-        slot = (q % warps) * 32u + t * group + q / warps;
-      } else {
-        slot = first_wave + (pos - n_first);
-      }
-      order[slot] = i;
-    }
+    if (in) place_rank(r, base + (uint32_t)__popc(peers & ((1u << lane) - 1u)), i, group, order, coop_list);
     __syncthreads();  // keeps the block's warps within one window of the image
   }
 }

@@ -161,8 +161,9 @@ static inline bool pack_scene(const void* objects, int64_t len, int64_t stride, 
   struct Rec8 { double v[8]; };
   std::vector<Rec4> st;
   std::vector<uint16_t> st_idx;
-  // movers grouped by time class, keeping array order inside a class
-  std::map<std::pair<double, double>, int> class_of;
+  // movers grouped by time class, keeping array order inside a class.  The key is the bit pattern of (time0, time1):
+  // a NaN time would break the strict weak ordering a map of doubles needs.
+  std::map<std::pair<uint64_t, uint64_t>, int> class_of;
   std::vector<std::pair<double, double>> class_key;
   std::vector<std::vector<int>> class_y, class_g;
 
@@ -176,13 +177,16 @@ static inline bool pack_scene(const void* objects, int64_t len, int64_t stride, 
       st.push_back(Rec4{{c[0], c[1], c[2], -W}});
       st_idx.push_back((uint16_t)i);
     } else {
-      auto key = std::make_pair(h.time0, h.time1);
+      uint64_t b0, b1;
+      memcpy(&b0, &h.time0, 8);
+      memcpy(&b1, &h.time1, 8);
+      auto key = std::make_pair(b0, b1);
       auto it = class_of.find(key);
       int ci;
       if (it == class_of.end()) {
         ci = (int)class_key.size();
         class_of[key] = ci;
-        class_key.push_back(key);
+        class_key.push_back(std::make_pair(h.time0, h.time1));
         class_y.emplace_back();
         class_g.emplace_back();
       } else {
