@@ -31,9 +31,14 @@ def main():
     h, w, spp = 675, 1200, 500
     cv = T.newCanvas(h, w, spp, 2.2)
     settings = [("off", {"TOR_BVH_COOP_MAX": 0})]
-    for alpha in ((2,) if QUICK else (1, 2, 3, 5)):
-        for mx in ((25,) if QUICK else (10, 25, 50)):
-            settings.append((f"alpha{alpha}_max{mx}", {"TOR_BVH_COOP_ALPHA": alpha, "TOR_BVH_COOP_MAX": mx}))
+    if QUICK:
+        settings.append(("default", {}))
+    else:
+        settings.append(("spread_a2", {"TOR_BVH_COOP_MODE": 0, "TOR_BVH_COOP_ALPHA": 2}))
+        for wc in (1, 2, 4):
+            for alpha in (2, 3):
+                settings.append((f"excl_wc{wc}_a{alpha}", {"TOR_BVH_COOP_MODE": 1, "TOR_BVH_COOP_WC": wc,
+                                                           "TOR_BVH_COOP_ALPHA": alpha}))
     out = {}
     for name, env in settings:
         ctx = ctx_with(env)

@@ -41,6 +41,8 @@ struct Tuning {
   long long coop_force = -1;   // TOR_BVH_COOP_FORCE: trace exactly this many of the most expensive pixels
                                //   cooperatively (tests), still capped by coop_max_pct
   int prepass_min_spp = 256;   // TOR_BVH_PREPASS_SPP: samples per pixel from which the cost pre-pass runs
+  int coop_mode = 1;           // TOR_BVH_COOP_MODE: 0 = cooperative warps spread over all CTAs, 1 = whole SMs set aside
+  int coop_wc = 4;             // TOR_BVH_COOP_WC: cooperative warps per CTA of a set-aside SM (1, 2, 4 or 8)
 
   static Tuning from_env() {
     Tuning t;
@@ -73,6 +75,11 @@ struct Tuning {
     t.coop_max_pct = clampi(geti("TOR_BVH_COOP_MAX", 25), 0, 50);
     if (const char* e = getenv("TOR_BVH_COOP_FORCE")) t.coop_force = atoll(e);
     t.prepass_min_spp = clampi(geti("TOR_BVH_PREPASS_SPP", 256), 9, 1 << 30);
+    t.coop_mode = geti("TOR_BVH_COOP_MODE", 1) ? 1 : 0;
+    {
+      int w = geti("TOR_BVH_COOP_WC", 4);
+      t.coop_wc = (w == 1 || w == 2 || w == 4 || w == 8) ? w : 4;
+    }
     return t;
   }
 };
@@ -482,7 +489,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
         if (d.d_order) cudaFree(d.d_order);
         d.d_cost = d.d_order = nullptr;
         d.order_cap = 0;
-        TOR_CUDA(ctx, cudaMalloc(&d.d_cost, slots * sizeof(uint32_t)));
+        TOR_CUDA(ctx, cudaMalloc(&d.d_cost, 2 * slots * sizeof(uint32_t)));  // raw estimates, then the smoothed ones
         TOR_CUDA(ctx, cudaMalloc(&d.d_order, slots * sizeof(uint32_t)));
         d.order_cap = slots;
       }
@@ -494,9 +501,16 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       // Warp-cooperative pixels: only in the default scheme, with the dealt wave, and never more than half the warps.
       // (TOR_BVH_COOP_FORCE lifts the cap to every pixel of the launch: the parity tests run whole images that way.)
       uint32_t coop_max = 0;
+      tor::CoopLayout lay;
+      lay.grid = (uint32_t)grid;
+      lay.wpc = (uint32_t)(block / 32);
+      lay.wc = (uint32_t)tune.coop_wc;
+      // whole SMs can only be set aside when the grid is exactly two CTAs on every SM
+      lay.mode = (tune.coop_mode == 1 && per_sm == 2 && grid == 2 * d.sm_count) ? 1u : 0u;
       if (coherent && warps && block == kBlock) {
-        coop_max = (uint32_t)((unsigned long long)warps_all * (unsigned)tune.coop_max_pct / 100ull);
-        if (coop_max > warps_all / 2) coop_max = warps_all / 2;
+        const unsigned long long slots = lay.mode ? (unsigned long long)grid * lay.wc : warps_all;
+        coop_max = (uint32_t)(slots * (unsigned)tune.coop_max_pct / 100ull);
+        if (coop_max > slots / 2) coop_max = (uint32_t)(slots / 2);
         if (tune.coop_force >= 0 && tune.coop_max_pct > 0) coop_max = n;
       }
       if (coop_max > d.coop_cap) {
@@ -520,12 +534,14 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       const uint32_t group = (uint32_t)tune.deal_group;
       const uint32_t force = tune.coop_force < 0 ? 0xffffffffu
                                                  : (uint32_t)(tune.coop_force > 0x7fffffffll ? 0x7fffffffll : tune.coop_force);
-      tor::cost_histogram_kernel<<<sort_grid, 256, 0, stream>>>(d.d_cost, n, d.d_hist, coherent ? 1u : 0u);
+      uint32_t* const d_rank_cost = d.d_cost + d.order_cap;  // what the ranking uses (cost_smooth_kernel)
+      tor::cost_smooth_kernel<<<sort_grid, 256, 0, stream>>>(d.d_cost, d_rank_cost, n, (uint32_t)ncols);
+      tor::cost_histogram_kernel<<<sort_grid, 256, 0, stream>>>(d_rank_cost, n, d.d_hist, coherent ? 1u : 0u);
       tor::cost_offsets_kernel<<<1, tor::kCostBuckets, 0, stream>>>(d.d_hist, d.d_sched, coherent ? 1u : 0u, lanes,
                                                                     tune.coop_alpha, coop_max, force);
       if (coherent) {
-        tor::cost_scatter_ordered_kernel<<<8, 1024, 0, stream>>>(d.d_cost, n, d.d_hist, d.d_order, warps, group, 1u,
-                                                              d.d_sched, d.d_coop);
+        tor::cost_scatter_ordered_kernel<<<8, 1024, 0, stream>>>(d_rank_cost, n, d.d_hist, d.d_order, warps, group, 1u,
+                                                              d.d_sched, d.d_coop, lay);
         main_plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin, /*chunked=*/true, /*coop=*/coop_max > 0,
                                  tune.block);
         TOR_CUDA(ctx, cudaFuncSetAttribute(main_plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -533,15 +549,16 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
         P.chunk = 32;
         P.chunk_guard = 0;
       } else {
-        tor::cost_scatter_kernel<<<sort_grid, 256, 0, stream>>>(d.d_cost, n, d.d_hist, d.d_order, warps, group,
-                                                                d.d_sched, d.d_coop);
+        tor::cost_scatter_kernel<<<sort_grid, 256, 0, stream>>>(d_rank_cost, n, d.d_hist, d.d_order, warps, group,
+                                                                d.d_sched, d.d_coop, lay);
       }
       TOR_CUDA(ctx, cudaGetLastError());
-      ctx->launches += 4;
+      ctx->launches += 5;
       P.order = d.d_order;
       P.first_wave = warps * 32u;
       P.sched = d.d_sched;  // sched[0] = 0 when coop_max == 0
       P.coop_list = d.d_coop;
+      P.coop = lay;
     } else if (reorder && sub_log2 == 0 && !tune.no_scramble) {
       // exact mode without cost information (few samples per pixel): scatter the image over the warps so that
       // expensive neighbours do not share one (BvhRenderParams::scramble).  Split-stream units are short, so there

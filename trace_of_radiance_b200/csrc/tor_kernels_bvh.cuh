@@ -29,6 +29,69 @@
 
 namespace tor {
 
+// Which warps of the render grid start cooperatively (one expensive pixel per warp, see the kernel) and which are
+// dealt pixels lane by lane.  Shared by the render kernel and the scatter kernels that lay the ranked pixels out.
+//   mode 0 "spread": cooperative warps are the first min(K, warps) ranks, rank = warp-in-CTA * grid + CTA, i.e. one per
+//          CTA before any CTA gets a second one.
+//   mode 1 "exclusive": whole SMs are set aside.  The grid is 2 CTAs per SM and CTAs b and b + grid/2 are taken to
+//          share an SM (the block scheduler fills the SMs breadth-first; nothing breaks if it does not, the warps
+//          merely share schedulers with other work).  The first ceil(K / (2 * wc)) SMs run `wc` cooperative warps per
+//          CTA and nothing else until those are done: a cooperative warp is a serial dependency chain, and every
+//          other warp on its scheduler takes issue slots from it.
+struct CoopLayout {
+  uint32_t mode, grid, wpc, wc;  // wpc = warps per CTA, wc = cooperative warps per cooperative CTA (mode 1)
+};
+struct WarpRole {
+  uint32_t coop_first, coop_stride;  // cooperative pixels coop_first, coop_first + coop_stride, ... < K (0xffffffff: none)
+  uint32_t deal_rank;                // 0xffffffff: this warp is dealt nothing
+  bool coop_cta;                     // mode 1: the CTA waits on a named barrier until its cooperative warps are done
+};
+__host__ __device__ __forceinline__ uint32_t coop_sms(const CoopLayout& c, uint32_t K) {
+  const uint32_t n_sm = c.grid / 2u, per_sm = 2u * c.wc;
+  const uint32_t want = (K + per_sm - 1u) / per_sm;
+  return want < n_sm ? want : n_sm;
+}
+// number of warps that are dealt pixels when K pixels are cooperative
+__host__ __device__ __forceinline__ uint32_t deal_warps(const CoopLayout& c, uint32_t K) {
+  const uint32_t warps = c.grid * c.wpc;
+  if (c.mode == 0u) return warps - (K < warps ? K : warps);
+  return (c.grid - 2u * coop_sms(c, K)) * c.wpc;
+}
+__device__ __forceinline__ WarpRole warp_role(const CoopLayout& c, uint32_t K, uint32_t b, uint32_t w) {
+  WarpRole r;
+  r.coop_first = 0xffffffffu;
+  r.coop_stride = 1u;
+  r.coop_cta = false;
+  if (c.mode == 0u) {
+    const uint32_t warps = c.grid * c.wpc, cw = K < warps ? K : warps, rank = w * c.grid + b;
+    if (rank < cw) {
+      r.coop_first = rank;
+      r.coop_stride = warps;
+      r.deal_rank = 0xffffffffu;
+    } else {
+      r.deal_rank = rank - cw;
+    }
+    return r;
+  }
+  const uint32_t n_sm = c.grid / 2u, sm = b % n_sm, half = b / n_sm, n_csm = coop_sms(c, K);
+  if (sm < n_csm) {
+    r.coop_cta = true;
+    r.deal_rank = 0xffffffffu;
+    // the two CTAs of an SM take different warp indices so that their cooperative warps sit on different schedulers
+    // when wc < 4 (warp slot mod 4 selects the scheduler)
+    const uint32_t w0 = (half * c.wc) % c.wpc;
+    const uint32_t k = (w + c.wpc - w0) % c.wpc;  // position among this CTA's cooperative warps
+    if (k < c.wc) {
+      const uint32_t n_cta = 2u * n_csm;
+      r.coop_first = k * n_cta + (sm * 2u + half);  // the most expensive pixels go to different SMs
+      r.coop_stride = n_cta * c.wc;
+    }
+  } else {
+    r.deal_rank = ((sm - n_csm) * 2u + half) * c.wpc + w;
+  }
+  return r;
+}
+
 struct BvhRenderParams {
   BvhView bv;
   const uint8_t* blob;  // device copy of PackedBvh::blob
@@ -65,6 +128,7 @@ struct BvhRenderParams {
   // ordinary queue afterwards.  NULL = no cooperative pixels.
   const uint32_t* sched;
   const uint32_t* coop_list;
+  CoopLayout coop;
   // Lanes of each warp that take pixels (1..32; 32 unless the TOR_BVH_LANES tuning knob says otherwise).
   int32_t lanes_per_warp;
   // Split-stream mode (TOR_MODE_FAST, include/tor_b200.h): every pixel's sample loop is cut into 2^sub_log2
@@ -176,7 +240,6 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   const float* __restrict__ cboxes = reinterpret_cast<const float*>((STAGE >= 1 ? smem : P.blob) + bv.off_cboxes);
   const float* __restrict__ oboxes = reinterpret_cast<const float*>((STAGE >= 1 ? smem : P.blob) + bv.off_oboxes);
   const uint32_t cboxes_sa = smem_u32(smem) + bv.off_cboxes, oboxes_sa = smem_u32(smem) + bv.off_oboxes;
-  __shared__ uint32_t coop_cand[COOP ? BLOCK / 32 : 1][32];  // candidate records of each cooperative warp
 
   __shared__ unsigned long long warp_chunk[CHUNKED ? BLOCK / 32 : 1][2];  // [next, end) slots of each warp's chunk
   unsigned long long* const wchunk = warp_chunk[CHUNKED ? tid >> 5 : 0];
@@ -189,10 +252,17 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   const unsigned long long total_units = total_px << P.sub_log2;
   // Layout of the cost-ranked order (see BvhRenderParams): [dealt: 32 per non-cooperative warp][queue]
   const uint32_t n_coop = (COOP && P.sched) ? P.sched[0] : 0u;  // cooperative pixels
-  const uint32_t grid_warps = gridDim.x * (uint32_t)(BLOCK / 32);
-  const uint32_t coop_warps = n_coop < grid_warps ? n_coop : grid_warps;  // warps that start cooperatively
-  const uint32_t wrank = (uint32_t)(tid >> 5) * gridDim.x + blockIdx.x;   // this warp's rank; < coop_warps: cooperative
-  const uint32_t first_wave = P.first_wave ? (grid_warps - coop_warps) * 32u : 0u;
+  WarpRole role;
+  if (COOP) {
+    role = warp_role(P.coop, n_coop, blockIdx.x, (uint32_t)(tid >> 5));
+  } else {  // no cooperative pixels: every warp is dealt its 32 entries
+    role.coop_first = 0xffffffffu;
+    role.coop_stride = 1u;
+    role.coop_cta = false;
+    role.deal_rank = (uint32_t)(tid >> 5) * gridDim.x + blockIdx.x;
+  }
+  const uint32_t first_wave =
+      P.first_wave ? (COOP ? deal_warps(P.coop, n_coop) : gridDim.x * (uint32_t)(BLOCK / 32)) * 32u : 0u;
   const uint32_t n_ranked = (uint32_t)total_px - n_coop;  // pixels that go to single lanes
   // length of the shared queue: everything, or what the cost-ranked order leaves after the dealt first wave
   const unsigned long long queue_len =
@@ -355,120 +425,128 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   // stream, same arithmetic, hence the same bits — nothing is broadcast), and the lanes share the only part of a
   // segment that has parallelism, the closest-hit search:
   //   1. 32 cluster boxes per step (a cluster = 32 consecutive tree records), float32 slab test;
-  //   2. the 32 object boxes of every cluster the ray enters; survivors are appended to a candidate list;
-  //   3. one candidate per lane through the reference's float64 sphere test (test_rec), all at once;
+  //   2. the 32 object boxes of every cluster the ray enters; a lane remembers the records whose box it saw entered;
+  //   3. the remembered candidates through the reference's float64 sphere test (test_rec), all lanes at once;
   //   4. argmin over the lanes of (t, original index) — the order-free form of hittables_lists.nim:48-55 — with
   //      three warp reductions on the bit pattern of t (monotonic: t_min < t <= +inf).
   // Shading then runs on all lanes redundantly (converged, one pass).  The set of objects tested is a superset of
   // the objects with a root (same padded boxes as the tree), so the hit is the lane mode's, bit for bit.
   if constexpr (COOP) {
-    if (wrank < coop_warps) {  // warp-uniform
+    if (role.coop_first != 0xffffffffu) {  // warp-uniform
       const int lane = tid & 31;
-      const unsigned lt_mask = (1u << lane) - 1u;
-      uint32_t* const cand = coop_cand[tid >> 5];
-      uint32_t ncand = 0;  // warp-uniform
-      // all listed candidates through the exact test, one per lane
-      auto flush = [&]() {
-        __syncwarp();
-        if ((uint32_t)lane < ncand) test_rec((int32_t)cand[lane]);
-        __syncwarp();
-        if (lane == 0) test_count += ncand;
-        ncand = 0;
-      };
-      // every lane with `has` appends `val`; the list never holds more than 32 entries
-      auto push = [&](bool has, uint32_t val) {
-        const unsigned m = __ballot_sync(0xffffffffu, has);
-        const uint32_t cnt = (uint32_t)__popc(m);
-        if (ncand + cnt > 32u) flush();
-        if (has) cand[ncand + (uint32_t)__popc(m & lt_mask)] = val;
-        ncand += cnt;
-      };
-      // one pixel per warp in a real render (n_coop <= warps); more only when a test forces it
-      for (uint32_t cr = wrank; cr < n_coop; cr += grid_warps) {
-      pid = P.coop_list[cr];
-      {
-        const int32_t ri = (int32_t)(pid / (uint32_t)P.ncols);
-        L.col = (int32_t)(pid - (uint32_t)ri * (uint32_t)P.ncols);
-        L.row = P.row_begin + ri * P.row_step;
-      }
-      rng_seed_pixel(L.rng, L.row, L.col, 0);  // render.nim:59-60
-      L.pix = v3(0, 0, 0);
-      for (int32_t s = 0; s < P.spp; ++s) {  // render.nim:62
-        start_sample(L, P.cam, P.nrows, P.ncols);
-        if (lane == 0) ++ray_count;
-        V3 color = v3(0, 0, 0);
-        for (;;) {  // render.nim:25-47, one bounce segment per pass
-          if (lane == 0) ++seg_count;
-          ray_setup();
-          for (int32_t base = bv.n_tree_objs; base < bv.n_objects; base += 32)  // objects without a finite box
-            push(base + lane < bv.n_objects, (uint32_t)(base + lane));
-          for (int32_t cb = 0; cb < bv.n_clusters; cb += 32) {
-            const int32_t c = cb + lane;
-            bool h = false;
-            if (c < bv.n_clusters)
-              h = slab_hit(ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, c), ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, bv.ncl_pad + c),
-                           ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 2 * bv.ncl_pad + c),
-                           ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 3 * bv.ncl_pad + c),
-                           ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 4 * bv.ncl_pad + c),
-                           ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 5 * bv.ncl_pad + c));
-            unsigned hit_clusters = __ballot_sync(0xffffffffu, h);
-            if (lane == 0) ++box_count;
-            while (hit_clusters) {
-              const int32_t ci = cb + __ffs(hit_clusters) - 1;
-              hit_clusters &= hit_clusters - 1u;
-              const int32_t obj = ci * 32 + lane;
-              const int32_t ob = ci * 192 + lane;
-              bool ho = false;
-              if (obj < bv.n_tree_objs)
-                ho = slab_hit(ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 32),
-                              ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 64), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 96),
-                              ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 128), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 160));
-              if (lane == 0) ++box_count;
-              push(ho, (uint32_t)obj);
-            }
-          }
-          flush();
-          // closest hit of the warp: lexicographic minimum of (t, original index)
-          {
-            const unsigned long long tb = (unsigned long long)__double_as_longlong(best_t);
-            const uint32_t hi = (uint32_t)(tb >> 32), lo = (uint32_t)tb;
-            const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
-            const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
-            const bool is_min = hi == mhi && lo == mlo;
-            const uint32_t morig = __reduce_min_sync(0xffffffffu, is_min ? best_orig : 0xffffffffu);
-            const unsigned win = __ballot_sync(0xffffffffu, is_min && best_orig == morig);
-            best_rec = __shfl_sync(0xffffffffu, best_rec, __ffs(win) - 1);
-            best_t = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | (unsigned long long)mlo));
-          }
-          if (best_rec < 0) {
-            color = shade_miss(L);
-            break;
-          }
-          const double2* __restrict__ r = recs + kRecStride16 * best_rec;
-          const double2 a2 = r[2], a6 = r[6], a7 = r[7];
-          const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
-          Surface S;
-          S.center = rec_center(r, kind_mat, L.time, qc);  // moving_spheres.nim:61
-          S.inv_r = a2.y;
-          S.albedo = v3(a6.x, a6.y, a7.x);
-          S.fuzz_or_ior = a7.y;
-          S.mat_kind = (kind_mat >> 8) & 0xffu;
-          if (shade_hit(L, best_t, S, P.max_depth)) break;  // absorbed or depth exhausted: black
+      const int32_t n_always = bv.n_objects - bv.n_tree_objs;
+      // one pixel per warp in a real render; more only when a test forces more cooperative pixels than warps
+      for (uint32_t cr = role.coop_first; cr < n_coop; cr += role.coop_stride) {
+        pid = P.coop_list[cr];
+        {
+          const int32_t ri = (int32_t)(pid / (uint32_t)P.ncols);
+          L.col = (int32_t)(pid - (uint32_t)ri * (uint32_t)P.ncols);
+          L.row = P.row_begin + ri * P.row_step;
         }
-        L.pix.x += color.x;  // render.nim:67
-        L.pix.y += color.y;
-        L.pix.z += color.z;
+        rng_seed_pixel(L.rng, L.row, L.col, 0);  // render.nim:59-60
+        L.pix = v3(0, 0, 0);
+        for (int32_t s = 0; s < P.spp; ++s) {  // render.nim:62
+          start_sample(L, P.cam, P.nrows, P.ncols);
+          if (lane == 0) ++ray_count;
+          V3 color = v3(0, 0, 0);
+          for (;;) {  // render.nim:25-47, one bounce segment per pass
+            if (lane == 0) ++seg_count;
+            ray_setup();
+            // Candidate records of this lane, kept in registers: a lane whose object box is entered in a cluster
+            // round remembers the record, and the exact tests run afterwards, all lanes together.  Objects without a
+            // finite box ("always" list: the ground sphere) start out as the candidates of the top lanes.  More
+            // than three candidates in one lane, or more than 32 always-objects, fall back to testing every record.
+            int32_t p0 = -1, p1 = -1, p2 = -1;
+            bool overflow = n_always > 32;
+            if (lane >= 32 - n_always) p0 = bv.n_tree_objs + (31 - lane);
+            for (int32_t cb = 0; cb < bv.n_clusters; cb += 32) {
+              const int32_t c = cb + lane;
+              bool h = false;
+              if (c < bv.n_clusters)
+                h = slab_hit(ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, c), ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, bv.ncl_pad + c),
+                             ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 2 * bv.ncl_pad + c),
+                             ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 3 * bv.ncl_pad + c),
+                             ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 4 * bv.ncl_pad + c),
+                             ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 5 * bv.ncl_pad + c));
+              unsigned hit_clusters = __ballot_sync(0xffffffffu, h);
+              if (lane == 0) box_count += 1u + (uint32_t)__popc(hit_clusters);
+              while (hit_clusters) {
+                const int32_t ci = cb + __ffs(hit_clusters) - 1;
+                hit_clusters &= hit_clusters - 1u;
+                const int32_t obj = ci * 32 + lane;
+                const int32_t ob = ci * 192 + lane;
+                if (obj < bv.n_tree_objs &&
+                    slab_hit(ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 32),
+                             ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 64), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 96),
+                             ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 128), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 160))) {
+                  overflow = overflow || p2 >= 0;
+                  p2 = p1 >= 0 ? obj : p2;
+                  p1 = (p0 >= 0 && p1 < 0) ? obj : p1;
+                  p0 = p0 < 0 ? obj : p0;
+                }
+              }
+            }
+            __syncwarp();
+            // the reference's test on the candidates: usually one pass, every lane with a candidate at once
+            for (int k = 0; k < 3; ++k) {
+              const int32_t cand = k == 0 ? p0 : (k == 1 ? p1 : p2);
+              if (!__any_sync(0xffffffffu, cand >= 0)) break;
+              if (cand >= 0) {
+                test_rec(cand);
+                ++test_count;
+              }
+              __syncwarp();
+            }
+            if (__any_sync(0xffffffffu, overflow)) {
+              for (int32_t ri = lane; ri < bv.n_objects; ri += 32) {
+                test_rec(ri);
+                ++test_count;
+              }
+              __syncwarp();
+            }
+            // closest hit of the warp: lexicographic minimum of (t, original index)
+            {
+              const unsigned long long tb = (unsigned long long)__double_as_longlong(best_t);
+              const uint32_t hi = (uint32_t)(tb >> 32), lo = (uint32_t)tb;
+              const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+              const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+              const bool is_min = hi == mhi && lo == mlo;
+              const uint32_t morig = __reduce_min_sync(0xffffffffu, is_min ? best_orig : 0xffffffffu);
+              const unsigned win = __ballot_sync(0xffffffffu, is_min && best_orig == morig);
+              best_rec = __shfl_sync(0xffffffffu, best_rec, __ffs(win) - 1);
+              best_t = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | (unsigned long long)mlo));
+            }
+            if (best_rec < 0) {
+              color = shade_miss(L);
+              break;
+            }
+            const double2* __restrict__ r = recs + kRecStride16 * best_rec;
+            const double2 a2 = r[2], a6 = r[6], a7 = r[7];
+            const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
+            Surface S;
+            S.center = rec_center(r, kind_mat, L.time, qc);  // moving_spheres.nim:61
+            S.inv_r = a2.y;
+            S.albedo = v3(a6.x, a6.y, a7.x);
+            S.fuzz_or_ior = a7.y;
+            S.mat_kind = (kind_mat >> 8) & 0xffu;
+            if (shade_hit(L, best_t, S, P.max_depth)) break;  // absorbed or depth exhausted: black
+          }
+          L.pix.x += color.x;  // render.nim:67
+          L.pix.y += color.y;
+          L.pix.z += color.z;
+        }
+        if (lane == 0) {
+          double* out = P.pixels + 3ull * pid;  // the sum; draw_kernel applies canvas.nim:47-54 afterwards
+          out[0] = L.pix.x;
+          out[1] = L.pix.y;
+          out[2] = L.pix.z;
+        }
+        __syncwarp();
       }
-      if (lane == 0) {
-        double* out = P.pixels + 3ull * pid;  // the sum; draw_kernel applies canvas.nim:47-54 afterwards
-        out[0] = L.pix.x;
-        out[1] = L.pix.y;
-        out[2] = L.pix.z;
-      }
-      __syncwarp();
-      }
-      first_fetch = false;  // cooperative warps were dealt nothing; they join the queue now
     }
+    // An SM set aside for cooperative warps (CoopLayout mode 1): its other warps take no work until those are done.
+    if (role.coop_cta) asm volatile("bar.sync 1, %0;" ::"n"(BLOCK) : "memory");
+    if (role.deal_rank == 0xffffffffu) first_fetch = false;  // dealt nothing: straight to the queue
   }
 
   for (;;) {
@@ -527,8 +605,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
         for (;;) {
           if (first_fetch) {  // dealt pixel of this lane, if any
             first_fetch = false;
-            const uint32_t gid = (wrank - coop_warps) * 32u + (uint32_t)(tid & 31);
-            pid = (wrank >= coop_warps && gid < first_wave) ? P.order[gid] : 0xffffffffu;
+            const uint32_t gid = role.deal_rank * 32u + (uint32_t)(tid & 31);
+            pid = (role.deal_rank != 0xffffffffu && gid < first_wave) ? P.order[gid] : 0xffffffffu;
             if (pid == 0xffffffffu) continue;
           } else if (P.first_wave) {
             const unsigned long long slot = atomicAdd(P.work_counter, 1ull);
@@ -549,8 +627,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
       // the same few materials.  Warp-uniform loop: each pass hands one slot to every lane that still needs one.
       if (first_fetch) {  // cost-ranked order: the pixel dealt to this lane, if any
         first_fetch = false;
-        const uint32_t gid = (wrank - coop_warps) * 32u + (uint32_t)(tid & 31);
-        pid = (need_pixel && wrank >= coop_warps && gid < first_wave) ? P.order[gid] : 0xffffffffu;
+        const uint32_t gid = role.deal_rank * 32u + (uint32_t)(tid & 31);
+        pid = (need_pixel && role.deal_rank != 0xffffffffu && gid < first_wave) ? P.order[gid] : 0xffffffffu;
         if (pid != 0xffffffffu) need_pixel = !begin_unit();
       }
       for (;;) {
@@ -728,6 +806,25 @@ __device__ __forceinline__ uint32_t cost_class(uint32_t c, uint32_t coarse) {
   return c < (uint32_t)kCostBuckets ? c : (uint32_t)kCostBuckets - 1u;
 }
 
+// The pre-pass costs are 8-sample estimates of a 500-sample total: a third of the truly expensive pixels come out at
+// half their cost or less, and ONE expensive pixel that is ranked as cheap and left to a single lane sets the
+// duration of the whole launch.  Expensive pixels come in patches (a glass sphere, an interreflecting corner), so the
+// ranking uses  max(own estimate, mean of the 2*kCostWindow+1 estimates around it in its row):  the mean has a
+// quarter of the noise, the max keeps isolated spikes and patch edges.
+static constexpr int kCostWindow = 3;
+__global__ void __launch_bounds__(256) cost_smooth_kernel(const uint32_t* __restrict__ cost, uint32_t* __restrict__ out,
+                                                          uint32_t n, uint32_t ncols) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t col = i % ncols;
+    const uint32_t lo = col >= (uint32_t)kCostWindow ? col - kCostWindow : 0u;
+    const uint32_t hi = col + kCostWindow < ncols ? col + kCostWindow : ncols - 1u;
+    uint32_t sum = 0;
+    for (uint32_t c = lo; c <= hi; ++c) sum += cost[i - col + c];
+    const uint32_t mean = sum / (hi - lo + 1u), own = cost[i];
+    out[i] = own > mean ? own : mean;
+  }
+}
+
 __global__ void __launch_bounds__(256) cost_histogram_kernel(const uint32_t* __restrict__ cost, uint32_t n,
                                                              uint32_t* __restrict__ hist, uint32_t coarse) {
   __shared__ uint32_t h[kCostBuckets];
@@ -802,10 +899,10 @@ struct RankLayout {
   uint32_t n_coop, warps, first_wave, tier, n_first;
 };
 __device__ __forceinline__ RankLayout rank_layout(const uint32_t* __restrict__ sched, uint32_t n, uint32_t warps_all,
-                                                  uint32_t group) {
+                                                  uint32_t group, const CoopLayout& coop) {
   RankLayout r;
   r.n_coop = sched ? sched[0] : 0u;
-  r.warps = warps_all ? warps_all - (r.n_coop < warps_all ? r.n_coop : warps_all) : 0u;  // warps that are dealt pixels
+  r.warps = warps_all ? (sched ? deal_warps(coop, r.n_coop) : warps_all) : 0u;  // warps that are dealt pixels
   r.first_wave = r.warps * 32u;
   r.tier = r.warps * group;
   const uint32_t n_ranked = n - r.n_coop;
@@ -833,8 +930,8 @@ __global__ void __launch_bounds__(256) cost_scatter_kernel(const uint32_t* __res
                                                            uint32_t* __restrict__ offsets, uint32_t* __restrict__ order,
                                                            uint32_t warps_all, uint32_t group,
                                                            const uint32_t* __restrict__ sched,
-                                                           uint32_t* __restrict__ coop_list) {
-  const RankLayout r = rank_layout(sched, n, warps_all, group);
+                                                           uint32_t* __restrict__ coop_list, CoopLayout coop) {
+  const RankLayout r = rank_layout(sched, n, warps_all, group, coop);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint32_t c = cost[i];
     uint32_t pos = atomicAdd(&offsets[c < kCostBuckets ? c : kCostBuckets - 1], 1u);
@@ -874,8 +971,8 @@ __global__ void __launch_bounds__(1024) cost_scatter_ordered_kernel(const uint32
                                                                     uint32_t* __restrict__ order, uint32_t warps_all,
                                                                     uint32_t group, uint32_t coarse,
                                                                     const uint32_t* __restrict__ sched,
-                                                                    uint32_t* __restrict__ coop_list) {
-  const RankLayout r = rank_layout(sched, n, warps_all, group);
+                                                                    uint32_t* __restrict__ coop_list, CoopLayout coop) {
+  const RankLayout r = rank_layout(sched, n, warps_all, group, coop);
   const uint32_t lane = threadIdx.x & 31u;
   for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
     const uint32_t i = i0 + threadIdx.x;
