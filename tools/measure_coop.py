@@ -34,9 +34,10 @@ def main():
     if QUICK:
         settings.append(("default", {}))
     else:
-        settings.append(("spread_a2", {"TOR_BVH_COOP_MODE": 0, "TOR_BVH_COOP_ALPHA": 2}))
-        for wc in (1, 2, 4):
-            for alpha in (2, 3):
+        for alpha in (2, 3, 5):
+            settings.append((f"spread_a{alpha}", {"TOR_BVH_COOP_MODE": 0, "TOR_BVH_COOP_ALPHA": alpha}))
+        for wc in (2, 4):
+            for alpha in (2, 3, 5):
                 settings.append((f"excl_wc{wc}_a{alpha}", {"TOR_BVH_COOP_MODE": 1, "TOR_BVH_COOP_WC": wc,
                                                            "TOR_BVH_COOP_ALPHA": alpha}))
     out = {}

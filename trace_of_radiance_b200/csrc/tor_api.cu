@@ -43,6 +43,7 @@ struct Tuning {
   int prepass_min_spp = 256;   // TOR_BVH_PREPASS_SPP: samples per pixel from which the cost pre-pass runs
   int coop_mode = 1;           // TOR_BVH_COOP_MODE: 0 = cooperative warps spread over all CTAs, 1 = whole SMs set aside
   int coop_wc = 4;             // TOR_BVH_COOP_WC: cooperative warps per CTA of a set-aside SM (1, 2, 4 or 8)
+  int coop_px_per_lane = 4;    // TOR_BVH_COOP_PXLANE: cooperative pixels only when the launch has fewer pixels per lane
 
   static Tuning from_env() {
     Tuning t;
@@ -76,6 +77,7 @@ struct Tuning {
     if (const char* e = getenv("TOR_BVH_COOP_FORCE")) t.coop_force = atoll(e);
     t.prepass_min_spp = clampi(geti("TOR_BVH_PREPASS_SPP", 256), 9, 1 << 30);
     t.coop_mode = geti("TOR_BVH_COOP_MODE", 1) ? 1 : 0;
+    t.coop_px_per_lane = clampi(geti("TOR_BVH_COOP_PXLANE", 4), 0, 1 << 20);
     {
       int w = geti("TOR_BVH_COOP_WC", 4);
       t.coop_wc = (w == 1 || w == 2 || w == 4 || w == 8) ? w : 4;
@@ -507,7 +509,11 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       lay.wc = (uint32_t)tune.coop_wc;
       // whole SMs can only be set aside when the grid is exactly two CTAs on every SM
       lay.mode = (tune.coop_mode == 1 && per_sm == 2 && grid == 2 * d.sm_count) ? 1u : 0u;
-      if (coherent && warps && block == kBlock) {
+      // Only launches with few pixels per lane can end on a single pixel's chain (C2: a GPU's share in a 4- or
+      // 8-GPU render); with many pixels per lane the dealt first wave hides the chains, and the kernel variant
+      // without the cooperative code runs the lanes ~4 % faster (its register allocation is tighter).
+      const bool few_pixels = total_px < lanes * (unsigned long long)tune.coop_px_per_lane;
+      if (coherent && warps && block == kBlock && (few_pixels || tune.coop_force >= 0)) {
         const unsigned long long slots = lay.mode ? (unsigned long long)grid * lay.wc : warps_all;
         coop_max = (uint32_t)(slots * (unsigned)tune.coop_max_pct / 100ull);
         if (coop_max > slots / 2) coop_max = (uint32_t)(slots / 2);

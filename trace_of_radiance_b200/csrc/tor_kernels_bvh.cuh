@@ -208,6 +208,300 @@ __device__ __forceinline__ V3 rec_center(const double2* __restrict__ r, uint32_t
   return c0;
 }
 
+// Closest hit of the current bounce segment + the per-segment constants of the sphere test.
+struct Closest {
+  double a;       // d.d  (spheres.nim:30)
+  double best_t;  // closest root so far
+  float best_f;   // the same rounded up to float32
+  uint32_t best_orig;
+  int32_t best_rec;
+  QCache qc;
+};
+// The float32 ray of the slab tests: 1/d and o/d.
+struct SlabRay {
+  float idx, idy, idz, oix, oiy, oiz;
+};
+
+// One object (record ri) against the ray: the reference's arithmetic (spheres.nim:28-49 / moving_spheres.nim:39-67),
+// operation for operation.  r2 = radius*radius and dc = center1 - center0 were computed on the host with the same
+// IEEE operations.
+__device__ __forceinline__ void test_record(const double2* __restrict__ recs, int32_t ri, const V3 o, const V3 d,
+                                            double time, Closest& C) {
+  const double INF = __longlong_as_double(0x7ff0000000000000ll);
+  const double t_min = 0.001;  // render.nim:28
+  const double a = C.a;
+  const double2* __restrict__ r = recs + kRecStride16 * ri;
+  const double2 a1 = r[1], a2 = r[2];
+  const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
+  const uint32_t orig = (uint32_t)((unsigned long long)__double_as_longlong(a2.x) >> 32);
+  V3 oc = o - rec_center(r, kind_mat, time, C.qc);
+  double half_b = dot(oc, d);
+  double c = len2(oc) - a1.y;
+  double disc = half_b * half_b - a * c;
+  if (disc > 0) {
+    const double root = sqrt(disc);
+    const double x1 = -half_b - root, x2 = -half_b + root;  // the reference's two numerators (spheres.nim:37-48)
+    // Three shortcuts that skip IEEE divides without changing the outcome (division by a > 0 and rounding are
+    // monotonic; the 2^-40 margins cover the rounding of the products below):
+    //   x2 <= t_min*a*(1 - 2^-40)  =>  both roots round to <= t_min: no root in (t_min, inf)   [the sphere the
+    //                                   ray starts on, spheres behind the origin]
+    //   x1 >= best_t*a*(1 + 2^-40) =>  the first root is valid and strictly beyond the closest so far
+    //   x1 <= t_min*a*(1 - 2^-40)  =>  the first root rounds to <= t_min: go straight to the second
+    //                                   (a ray that starts on this sphere and crosses it: every glass-internal segment)
+    const bool a_ok = a >= 1e-200 && a <= 1e200;
+    const double ta_lo = (t_min * a) * (1.0 - 0x1p-40);
+    const double ba = C.best_t * a;
+    const bool none = a_ok && x2 <= ta_lo;
+    const bool behind = a_ok && x1 >= ba * (1.0 + 0x1p-40);
+    if (!none && !behind) {
+      double t = INF;
+      const bool skip1 = a_ok && x1 <= ta_lo;
+      double sol = skip1 ? 0.0 : x1 / a;
+      if (!skip1 && t_min < sol) {
+        t = sol;
+      } else {
+        sol = x2 / a;
+        if (t_min < sol) t = sol;
+      }
+      if (t < C.best_t || (t == C.best_t && orig < C.best_orig && t < INF)) {
+        C.best_t = t;
+        C.best_orig = orig;
+        C.best_rec = ri;
+        C.best_f = __double2float_ru(t);
+      }
+    }
+  }
+}
+
+// A new bounce segment: resets the closest hit and derives the float32 ray of the slab tests.  Components of d far
+// below the largest one are replaced by +-2^-60 * dmax (a direction change below 2^-60, negligible against the box
+// padding) so that 1/d stays finite; rays outside the range the padding was derived for test everything instead.
+__device__ __forceinline__ void setup_ray(const V3 o, const V3 d, float s_limit, Closest& C, SlabRay& R) {
+  C.best_t = __longlong_as_double(0x7ff0000000000000ll);
+  C.best_orig = 0xffffffffu;
+  C.best_rec = -1;
+  C.best_f = __int_as_float(0x7f800000);
+  C.qc.t0 = C.qc.t1 = __longlong_as_double(0x7ff8000000000000ll);  // NaN: never equal, forces the first divide
+  C.a = len2(d);
+  float dxf = __double2float_rn(d.x), dyf = __double2float_rn(d.y), dzf = __double2float_rn(d.z);
+  float oxf = __double2float_rn(o.x), oyf = __double2float_rn(o.y), ozf = __double2float_rn(o.z);
+  float dmax = fmaxf(fabsf(dxf), fmaxf(fabsf(dyf), fabsf(dzf)));
+  float omax = fmaxf(fabsf(oxf), fmaxf(fabsf(oyf), fabsf(ozf)));
+  bool ok = dmax >= 0x1p-40f && dmax <= 0x1p40f && omax <= s_limit;
+  ok = ok && dxf == dxf && dyf == dyf && dzf == dzf && oxf == oxf && oyf == oyf && ozf == ozf;
+  if (ok) {
+    float dmin = dmax * 0x1p-60f;
+    if (fabsf(dxf) < dmin) dxf = copysignf(dmin, dxf);
+    if (fabsf(dyf) < dmin) dyf = copysignf(dmin, dyf);
+    if (fabsf(dzf) < dmin) dzf = copysignf(dmin, dzf);
+    R.idx = __frcp_rn(dxf);
+    R.idy = __frcp_rn(dyf);
+    R.idz = __frcp_rn(dzf);
+    R.oix = oxf * R.idx;
+    R.oiy = oyf * R.idy;
+    R.oiz = ozf * R.idz;
+  } else {
+    R.idx = R.idy = R.idz = 0.f;  // every slab interval becomes [0, 0]: all boxes pass
+    R.oix = R.oiy = R.oiz = 0.f;
+  }
+}
+
+// The slab test of the traversal loop on one box (the same expression, so the same conservativeness argument).
+__device__ __forceinline__ bool slab_test(const SlabRay& R, float best_f, float lx, float ly, float lz, float hx,
+                                          float hy, float hz) {
+  const float ax0 = fmaf(lx, R.idx, -R.oix), ax1 = fmaf(hx, R.idx, -R.oix);
+  const float ay0 = fmaf(ly, R.idy, -R.oiy), ay1 = fmaf(hy, R.idy, -R.oiy);
+  const float az0 = fmaf(lz, R.idz, -R.oiz), az1 = fmaf(hz, R.idz, -R.oiz);
+  const float nr = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.f));
+  const float fr = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), best_f));
+  return nr <= fr;
+}
+
+// ================================================================= warp-cooperative pixels
+// A pixel's samples are one serial chain (render.nim:59-67), so the render cannot end before its most expensive
+// pixel does, and a single lane needs microseconds per bounce segment.  The n_coop most expensive pixels of the
+// cost pre-pass are therefore traced by a whole warp each: every lane carries the same path state (same RNG
+// stream, same arithmetic, hence the same bits — nothing is broadcast), and the lanes share the only part of a
+// segment that has parallelism, the closest-hit search:
+//   1. 32 cluster boxes per step (a cluster = 32 consecutive tree records), float32 slab test;
+//   2. the 32 object boxes of every cluster the ray enters; a lane remembers the records whose box it saw entered;
+//   3. the remembered candidates through the reference's float64 sphere test (test_rec), all lanes at once;
+//   4. argmin over the lanes of (t, original index) — the order-free form of hittables_lists.nim:48-55 — with
+//      three warp reductions on the bit pattern of t (monotonic: t_min < t <= +inf).
+// Shading then runs on all lanes redundantly (converged, one pass).  The set of objects tested is a superset of
+// the objects with a root (same padded boxes as the tree), so the hit is the lane mode's, bit for bit.
+template <int STAGE>
+__device__ __forceinline__ void coop_pixels(const BvhRenderParams& P, uint32_t coop_first, uint32_t coop_stride,
+                                         uint32_t n_coop) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const BvhView& bv = P.bv;
+  const double2* __restrict__ recs = reinterpret_cast<const double2*>((STAGE == 2 ? smem : P.blob) + bv.off_objs);
+  const float* __restrict__ cboxes = reinterpret_cast<const float*>((STAGE >= 1 ? smem : P.blob) + bv.off_cboxes);
+  const float* __restrict__ oboxes = reinterpret_cast<const float*>((STAGE >= 1 ? smem : P.blob) + bv.off_oboxes);
+  const uint32_t cboxes_sa = smem_u32(smem) + bv.off_cboxes, oboxes_sa = smem_u32(smem) + bv.off_oboxes;
+  Lane L;
+  L.pix = v3(0, 0, 0);
+  L.att = v3(1, 1, 1);
+  L.o = v3(0, 0, 0);
+  L.d = v3(0, 0, 1);
+  L.time = 0.0;
+  L.row = L.col = L.sample = L.depth = 0;
+  Closest C;
+  C.a = 1.0;
+  C.qc.t0 = C.qc.t1 = C.qc.q = 0.0;
+  SlabRay R;
+  unsigned long long seg_count = 0, ray_count = 0;
+  uint32_t box_count = 0, test_count = 0;
+  const int lane = threadIdx.x & 31;
+  const int32_t n_always = bv.n_objects - bv.n_tree_objs;
+  // one pixel per warp in a real render; more only when a test forces more cooperative pixels than warps
+  for (uint32_t cr = coop_first; cr < n_coop; cr += coop_stride) {
+    const uint32_t pid = P.coop_list[cr];
+    {
+      const int32_t ri = (int32_t)(pid / (uint32_t)P.ncols);
+      L.col = (int32_t)(pid - (uint32_t)ri * (uint32_t)P.ncols);
+      L.row = P.row_begin + ri * P.row_step;
+    }
+    rng_seed_pixel(L.rng, L.row, L.col, 0);  // render.nim:59-60
+    L.pix = v3(0, 0, 0);
+    for (int32_t s = 0; s < P.spp; ++s) {  // render.nim:62
+      start_sample(L, P.cam, P.nrows, P.ncols);
+      if (lane == 0) ++ray_count;
+      V3 color = v3(0, 0, 0);
+      for (;;) {  // render.nim:25-47, one bounce segment per pass
+        if (lane == 0) ++seg_count;
+        setup_ray(L.o, L.d, bv.s_limit, C, R);
+        // Candidate records of this lane, kept in registers: a lane whose object box is entered in a cluster
+        // round remembers the record, and the exact tests run afterwards, all lanes together.  Objects without a
+        // finite box ("always" list: the ground sphere) start out as the candidates of the top lanes.  More
+        // than three candidates in one lane, or more than 32 always-objects, fall back to testing every record.
+        int32_t p0 = -1, p1 = -1, p2 = -1;
+        bool overflow = n_always > 32;
+        if (lane >= 32 - n_always) p0 = bv.n_tree_objs + (31 - lane);
+        // one object-box test of this lane in cluster ci (ci < 0: none); branch-free so that the four tests of a
+        // pass overlap in the pipeline
+        auto obj_round = [&](int32_t ci) {
+          const int32_t cj = ci < 0 ? 0 : ci;
+          const int32_t obj = cj * 32 + lane;
+          const int32_t ob = cj * 192 + lane;
+          const bool in =
+              slab_test(R, C.best_f, ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 32),
+                       ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 64), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 96),
+                       ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 128), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 160));
+          return (ci >= 0 && obj < bv.n_tree_objs && in) ? obj : -1;
+        };
+        auto remember = [&](int32_t obj) {
+          const bool has = obj >= 0;
+          overflow = overflow || (has && p2 >= 0);
+          p2 = (has && p1 >= 0) ? obj : p2;
+          p1 = (has && p0 >= 0 && p1 < 0) ? obj : p1;
+          p0 = (has && p0 < 0) ? obj : p0;
+        };
+        for (int32_t cb = 0; cb < bv.n_clusters; cb += 32) {
+          const int32_t c = cb + lane;
+          const int32_t cc = c < bv.n_clusters ? c : 0;  // padding lanes read cluster 0 and are masked out
+          const bool h =
+              slab_test(R, C.best_f, ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, cc), ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, bv.ncl_pad + cc),
+                       ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 2 * bv.ncl_pad + cc),
+                       ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 3 * bv.ncl_pad + cc),
+                       ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 4 * bv.ncl_pad + cc),
+                       ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 5 * bv.ncl_pad + cc)) &&
+              c < bv.n_clusters;
+          unsigned hit_clusters = __ballot_sync(0xffffffffu, h);
+          if (lane == 0) box_count += 1u + (uint32_t)__popc(hit_clusters);
+          while (hit_clusters) {  // four entered clusters per pass
+            int32_t ci[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              ci[j] = hit_clusters ? cb + __ffs(hit_clusters) - 1 : -1;
+              hit_clusters &= hit_clusters - 1u;
+            }
+            int32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = obj_round(ci[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) remember(o[j]);
+          }
+        }
+        __syncwarp();
+        // the reference's test on the candidates: usually one pass, every lane with a candidate at once
+        if (p0 >= 0) {
+          test_record(recs, p0, L.o, L.d, L.time, C);
+          ++test_count;
+        }
+        __syncwarp();
+        if (__any_sync(0xffffffffu, p1 >= 0 || overflow)) {  // rare
+          for (int k = 1; k < 3; ++k) {
+            const int32_t cand = k == 1 ? p1 : p2;
+            if (cand >= 0) {
+              test_record(recs, cand, L.o, L.d, L.time, C);
+              ++test_count;
+            }
+            __syncwarp();
+          }
+          if (__any_sync(0xffffffffu, overflow)) {
+            for (int32_t ri = lane; ri < bv.n_objects; ri += 32) {
+              test_record(recs, ri, L.o, L.d, L.time, C);
+              ++test_count;
+            }
+            __syncwarp();
+          }
+        }
+        // closest hit of the warp: lexicographic minimum of (t, original index), then the winner's record
+        {
+          const unsigned long long tb = (unsigned long long)__double_as_longlong(C.best_t);
+          const uint32_t hi = (uint32_t)(tb >> 32), lo = (uint32_t)tb;
+          const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+          const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+          const bool is_min = hi == mhi && lo == mlo;
+          const uint32_t morig = __reduce_min_sync(0xffffffffu, is_min ? C.best_orig : 0xffffffffu);
+          // several lanes can hold the winner only when they hold the same record (original indices are unique)
+          C.best_rec = (int32_t)__reduce_min_sync(0xffffffffu, (is_min && C.best_orig == morig) ? (uint32_t)C.best_rec
+                                                                                              : 0xffffffffu);
+          C.best_t = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | (unsigned long long)mlo));
+        }
+        if (C.best_rec < 0) {
+          color = shade_miss(L);
+          break;
+        }
+        const double2* __restrict__ r = recs + kRecStride16 * C.best_rec;
+        const double2 a2 = r[2], a6 = r[6], a7 = r[7];
+        const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
+        Surface S;
+        S.center = rec_center(r, kind_mat, L.time, C.qc);  // moving_spheres.nim:61
+        S.inv_r = a2.y;
+        S.albedo = v3(a6.x, a6.y, a7.x);
+        S.fuzz_or_ior = a7.y;
+        S.mat_kind = (kind_mat >> 8) & 0xffu;
+        if (shade_hit(L, C.best_t, S, P.max_depth)) break;  // absorbed or depth exhausted: black
+      }
+      L.pix.x += color.x;  // render.nim:67
+      L.pix.y += color.y;
+      L.pix.z += color.z;
+    }
+    if (lane == 0) {
+      double* out = P.pixels + 3ull * pid;  // the sum; draw_kernel applies canvas.nim:47-54 afterwards
+      out[0] = L.pix.x;
+      out[1] = L.pix.y;
+      out[2] = L.pix.z;
+    }
+    __syncwarp();
+  }
+  if (P.count_segments) {
+    unsigned long long box_sum = box_count, test_sum = test_count;
+    for (int ofs = 16; ofs > 0; ofs >>= 1) {
+      box_sum += __shfl_down_sync(0xffffffffu, box_sum, ofs);
+      test_sum += __shfl_down_sync(0xffffffffu, test_sum, ofs);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(P.counters + 0, ray_count);
+      atomicAdd(P.counters + 1, seg_count);
+      atomicAdd(P.counters + 2, box_sum);
+      atomicAdd(P.counters + 3, test_sum);
+    }
+  }
+}
+
 template <int BLOCK, int STAGE, bool CHUNKED, bool COOP>
 __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_bvh_kernel(const __grid_constant__ BvhRenderParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -236,10 +530,6 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   const float4* __restrict__ nodes = reinterpret_cast<const float4*>((STAGE >= 1 ? smem : P.blob) + bv.off_nodes);
   const double2* __restrict__ recs = reinterpret_cast<const double2*>((STAGE == 2 ? smem : P.blob) + bv.off_objs);
   const uint32_t nodes_sa = smem_u32(smem) + bv.off_nodes;  // meaningful for STAGE >= 1 only
-  // box tables of the warp-cooperative search (COOP kernels only)
-  const float* __restrict__ cboxes = reinterpret_cast<const float*>((STAGE >= 1 ? smem : P.blob) + bv.off_cboxes);
-  const float* __restrict__ oboxes = reinterpret_cast<const float*>((STAGE >= 1 ? smem : P.blob) + bv.off_oboxes);
-  const uint32_t cboxes_sa = smem_u32(smem) + bv.off_cboxes, oboxes_sa = smem_u32(smem) + bv.off_oboxes;
 
   __shared__ unsigned long long warp_chunk[CHUNKED ? BLOCK / 32 : 1][2];  // [next, end) slots of each warp's chunk
   unsigned long long* const wchunk = warp_chunk[CHUNKED ? tid >> 5 : 0];
@@ -269,6 +559,14 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
       P.order ? (unsigned long long)(n_ranked - (n_ranked < first_wave ? n_ranked : first_wave)) : total_units;
   const int refill = P.refill;
 
+  // ================================================================= warp-cooperative pixels (coop_pixels above)
+  // Called before any lane state exists, so that the call keeps nothing alive across it.
+  if constexpr (COOP) {
+    if (role.coop_first != 0xffffffffu) coop_pixels<STAGE>(P, role.coop_first, role.coop_stride, n_coop);  // warp-uniform
+    // An SM set aside for cooperative warps (CoopLayout mode 1): its other warps take no work until those are done.
+    if (role.coop_cta) asm volatile("bar.sync 1, %0;" ::"n"(BLOCK) : "memory");
+  }
+
   Lane L;
   L.pix = v3(0, 0, 0);
   L.att = v3(1, 1, 1);
@@ -279,7 +577,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   uint32_t pid = 0;      // work unit: pixel index inside the selected rows (<< sub_log2 | sample range)
   uint32_t pix_seg = 0;  // bounce segments of the current unit
   bool active = false, need_pixel = (tid & 31) < P.lanes_per_warp, need_sample = false;
-  bool first_fetch = P.first_wave != 0;
+  bool first_fetch = P.first_wave != 0 && role.deal_rank != 0xffffffffu;  // warps that are dealt nothing go straight to the queue
   bool trav_done = false;  // the current segment's closest hit is final
   bool need_setup = false;  // a new segment needs its traversal state
   unsigned long long seg_count = 0, ray_count = 0;
@@ -289,104 +587,18 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   int2 stk[kBvhStackDepth];  // {child reference, float bits of the entry distance}: one 8-byte local access each
   int sp = 0;
   int32_t cur = 0;
-  float idx = 0.f, idy = 0.f, idz = 0.f, oix = 0.f, oiy = 0.f, oiz = 0.f;  // 1/d and o/d in float32
-  double a = 1.0;       // d.d  (spheres.nim:30)
-  double best_t = INF;  // closest root so far
-  float best_f = 0.f;   // the same rounded up to float32
-  uint32_t best_orig = 0xffffffffu;
-  int32_t best_rec = -1;
-  QCache qc;
-  qc.t0 = qc.t1 = qc.q = 0.0;
+  SlabRay R;  // 1/d and o/d in float32
+  R.idx = R.idy = R.idz = R.oix = R.oiy = R.oiz = 0.f;
+  Closest C;
+  C.a = 1.0;
+  C.best_t = INF;
+  C.best_f = 0.f;
+  C.best_orig = 0xffffffffu;
+  C.best_rec = -1;
+  C.qc.t0 = C.qc.t1 = C.qc.q = 0.0;
 
-  auto test_rec = [&](int32_t ri) {
-    const double2* __restrict__ r = recs + kRecStride16 * ri;
-    const double2 a1 = r[1], a2 = r[2];
-    const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
-    const uint32_t orig = (uint32_t)((unsigned long long)__double_as_longlong(a2.x) >> 32);
-    const V3 o = L.o, d = L.d;
-    V3 oc = o - rec_center(r, kind_mat, L.time, qc);
-    double half_b = dot(oc, d);
-    double c = len2(oc) - a1.y;
-    double disc = half_b * half_b - a * c;
-    if (disc > 0) {
-      const double root = sqrt(disc);
-      const double x1 = -half_b - root, x2 = -half_b + root;  // the reference's two numerators (spheres.nim:37-48)
-      // Two shortcuts that skip the IEEE divides without changing the outcome (division by a > 0 and rounding
-      // are monotonic; the 2^-40 margins cover the rounding of the products below):
-      //   x2 <= t_min*a*(1 - 2^-40)  =>  both roots round to <= t_min: no root in (t_min, inf)   [the sphere the
-      //                                   ray starts on, spheres behind the origin]
-      //   x1 >= best_t*a*(1 + 2^-40) =>  the first root is valid and strictly beyond the closest so far
-      //   x1 <= t_min*a*(1 - 2^-40)  =>  the first root rounds to <= t_min: go straight to the second
-      const bool a_ok = a >= 1e-200 && a <= 1e200;
-      const double ta = t_min * a;
-      const double ba = best_t * a;
-      const double ta_lo = ta * (1.0 - 0x1p-40);
-      const bool none = a_ok && x2 <= ta_lo;
-      const bool behind = a_ok && x1 >= ba * (1.0 + 0x1p-40);
-      if (!none && !behind) {
-        double t = INF;
-        // x1 <= t_min*a*(1 - 2^-40) => x1 / a rounds to <= t_min: the first root fails `t_min < sol` and only the
-        // second divide is needed (a ray that starts on this sphere and crosses it: every glass-internal segment)
-        const bool skip1 = a_ok && x1 <= ta_lo;
-        double sol = skip1 ? 0.0 : x1 / a;
-        if (!skip1 && t_min < sol) {
-          t = sol;
-        } else {
-          sol = x2 / a;
-          if (t_min < sol) t = sol;
-        }
-        if (t < best_t || (t == best_t && orig < best_orig && t < INF)) {
-          best_t = t;
-          best_orig = orig;
-          best_rec = ri;
-          best_f = __double2float_ru(t);
-        }
-      }
-    }
-  };
-
-  // A new bounce segment: resets the closest hit and derives the float32 ray of the slab tests.  Components of d far
-  // below the largest one are replaced by +-2^-60 * dmax (a direction change below 2^-60, negligible against the box
-  // padding) so that 1/d stays finite; rays outside the range the padding was derived for test everything instead.
-  auto ray_setup = [&]() {
-    best_t = INF;
-    best_orig = 0xffffffffu;
-    best_rec = -1;
-    best_f = __int_as_float(0x7f800000);
-    qc.t0 = qc.t1 = __longlong_as_double(0x7ff8000000000000ll);  // NaN: never equal, forces the first divide
-    const V3 o = L.o, d = L.d;
-    a = len2(d);
-    float dxf = __double2float_rn(d.x), dyf = __double2float_rn(d.y), dzf = __double2float_rn(d.z);
-    float oxf = __double2float_rn(o.x), oyf = __double2float_rn(o.y), ozf = __double2float_rn(o.z);
-    float dmax = fmaxf(fabsf(dxf), fmaxf(fabsf(dyf), fabsf(dzf)));
-    float omax = fmaxf(fabsf(oxf), fmaxf(fabsf(oyf), fabsf(ozf)));
-    bool ok = dmax >= 0x1p-40f && dmax <= 0x1p40f && omax <= bv.s_limit;
-    ok = ok && dxf == dxf && dyf == dyf && dzf == dzf && oxf == oxf && oyf == oyf && ozf == ozf;
-    if (ok) {
-      float dmin = dmax * 0x1p-60f;
-      if (fabsf(dxf) < dmin) dxf = copysignf(dmin, dxf);
-      if (fabsf(dyf) < dmin) dyf = copysignf(dmin, dyf);
-      if (fabsf(dzf) < dmin) dzf = copysignf(dmin, dzf);
-      idx = __frcp_rn(dxf);
-      idy = __frcp_rn(dyf);
-      idz = __frcp_rn(dzf);
-      oix = oxf * idx;
-      oiy = oyf * idy;
-      oiz = ozf * idz;
-    } else {
-      idx = idy = idz = 0.f;  // every slab interval becomes [0, 0]: all boxes pass
-      oix = oiy = oiz = 0.f;
-    }
-  };
-  // The slab test of the traversal loop on one box (the same expression, so the same conservativeness argument).
-  auto slab_hit = [&](float lx, float ly, float lz, float hx, float hy, float hz) -> bool {
-    const float ax0 = fmaf(lx, idx, -oix), ax1 = fmaf(hx, idx, -oix);
-    const float ay0 = fmaf(ly, idy, -oiy), ay1 = fmaf(hy, idy, -oiy);
-    const float az0 = fmaf(lz, idz, -oiz), az1 = fmaf(hz, idz, -oiz);
-    const float nr = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.f));
-    const float fr = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), best_f));
-    return nr <= fr;
-  };
+  auto test_rec = [&](int32_t ri) { test_record(recs, ri, L.o, L.d, L.time, C); };
+  auto ray_setup = [&]() { setup_ray(L.o, L.d, bv.s_limit, C, R); };
 
   // queue slot -> work unit when there is no cost-ranked order: consecutive slots are the sample ranges of one pixel;
   // the pixels come in row-major or scrambled order
@@ -418,137 +630,6 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
     return false;
   };
 
-  // ================================================================= warp-cooperative pixels
-  // A pixel's samples are one serial chain (render.nim:59-67), so the render cannot end before its most expensive
-  // pixel does, and a single lane needs microseconds per bounce segment.  The n_coop most expensive pixels of the
-  // cost pre-pass are therefore traced by a whole warp each: every lane carries the same path state (same RNG
-  // stream, same arithmetic, hence the same bits — nothing is broadcast), and the lanes share the only part of a
-  // segment that has parallelism, the closest-hit search:
-  //   1. 32 cluster boxes per step (a cluster = 32 consecutive tree records), float32 slab test;
-  //   2. the 32 object boxes of every cluster the ray enters; a lane remembers the records whose box it saw entered;
-  //   3. the remembered candidates through the reference's float64 sphere test (test_rec), all lanes at once;
-  //   4. argmin over the lanes of (t, original index) — the order-free form of hittables_lists.nim:48-55 — with
-  //      three warp reductions on the bit pattern of t (monotonic: t_min < t <= +inf).
-  // Shading then runs on all lanes redundantly (converged, one pass).  The set of objects tested is a superset of
-  // the objects with a root (same padded boxes as the tree), so the hit is the lane mode's, bit for bit.
-  if constexpr (COOP) {
-    if (role.coop_first != 0xffffffffu) {  // warp-uniform
-      const int lane = tid & 31;
-      const int32_t n_always = bv.n_objects - bv.n_tree_objs;
-      // one pixel per warp in a real render; more only when a test forces more cooperative pixels than warps
-      for (uint32_t cr = role.coop_first; cr < n_coop; cr += role.coop_stride) {
-        pid = P.coop_list[cr];
-        {
-          const int32_t ri = (int32_t)(pid / (uint32_t)P.ncols);
-          L.col = (int32_t)(pid - (uint32_t)ri * (uint32_t)P.ncols);
-          L.row = P.row_begin + ri * P.row_step;
-        }
-        rng_seed_pixel(L.rng, L.row, L.col, 0);  // render.nim:59-60
-        L.pix = v3(0, 0, 0);
-        for (int32_t s = 0; s < P.spp; ++s) {  // render.nim:62
-          start_sample(L, P.cam, P.nrows, P.ncols);
-          if (lane == 0) ++ray_count;
-          V3 color = v3(0, 0, 0);
-          for (;;) {  // render.nim:25-47, one bounce segment per pass
-            if (lane == 0) ++seg_count;
-            ray_setup();
-            // Candidate records of this lane, kept in registers: a lane whose object box is entered in a cluster
-            // round remembers the record, and the exact tests run afterwards, all lanes together.  Objects without a
-            // finite box ("always" list: the ground sphere) start out as the candidates of the top lanes.  More
-            // than three candidates in one lane, or more than 32 always-objects, fall back to testing every record.
-            int32_t p0 = -1, p1 = -1, p2 = -1;
-            bool overflow = n_always > 32;
-            if (lane >= 32 - n_always) p0 = bv.n_tree_objs + (31 - lane);
-            for (int32_t cb = 0; cb < bv.n_clusters; cb += 32) {
-              const int32_t c = cb + lane;
-              bool h = false;
-              if (c < bv.n_clusters)
-                h = slab_hit(ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, c), ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, bv.ncl_pad + c),
-                             ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 2 * bv.ncl_pad + c),
-                             ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 3 * bv.ncl_pad + c),
-                             ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 4 * bv.ncl_pad + c),
-                             ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 5 * bv.ncl_pad + c));
-              unsigned hit_clusters = __ballot_sync(0xffffffffu, h);
-              if (lane == 0) box_count += 1u + (uint32_t)__popc(hit_clusters);
-              while (hit_clusters) {
-                const int32_t ci = cb + __ffs(hit_clusters) - 1;
-                hit_clusters &= hit_clusters - 1u;
-                const int32_t obj = ci * 32 + lane;
-                const int32_t ob = ci * 192 + lane;
-                if (obj < bv.n_tree_objs &&
-                    slab_hit(ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 32),
-                             ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 64), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 96),
-                             ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 128), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 160))) {
-                  overflow = overflow || p2 >= 0;
-                  p2 = p1 >= 0 ? obj : p2;
-                  p1 = (p0 >= 0 && p1 < 0) ? obj : p1;
-                  p0 = p0 < 0 ? obj : p0;
-                }
-              }
-            }
-            __syncwarp();
-            // the reference's test on the candidates: usually one pass, every lane with a candidate at once
-            for (int k = 0; k < 3; ++k) {
-              const int32_t cand = k == 0 ? p0 : (k == 1 ? p1 : p2);
-              if (!__any_sync(0xffffffffu, cand >= 0)) break;
-              if (cand >= 0) {
-                test_rec(cand);
-                ++test_count;
-              }
-              __syncwarp();
-            }
-            if (__any_sync(0xffffffffu, overflow)) {
-              for (int32_t ri = lane; ri < bv.n_objects; ri += 32) {
-                test_rec(ri);
-                ++test_count;
-              }
-              __syncwarp();
-            }
-            // closest hit of the warp: lexicographic minimum of (t, original index)
-            {
-              const unsigned long long tb = (unsigned long long)__double_as_longlong(best_t);
-              const uint32_t hi = (uint32_t)(tb >> 32), lo = (uint32_t)tb;
-              const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
-              const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
-              const bool is_min = hi == mhi && lo == mlo;
-              const uint32_t morig = __reduce_min_sync(0xffffffffu, is_min ? best_orig : 0xffffffffu);
-              const unsigned win = __ballot_sync(0xffffffffu, is_min && best_orig == morig);
-              best_rec = __shfl_sync(0xffffffffu, best_rec, __ffs(win) - 1);
-              best_t = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | (unsigned long long)mlo));
-            }
-            if (best_rec < 0) {
-              color = shade_miss(L);
-              break;
-            }
-            const double2* __restrict__ r = recs + kRecStride16 * best_rec;
-            const double2 a2 = r[2], a6 = r[6], a7 = r[7];
-            const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
-            Surface S;
-            S.center = rec_center(r, kind_mat, L.time, qc);  // moving_spheres.nim:61
-            S.inv_r = a2.y;
-            S.albedo = v3(a6.x, a6.y, a7.x);
-            S.fuzz_or_ior = a7.y;
-            S.mat_kind = (kind_mat >> 8) & 0xffu;
-            if (shade_hit(L, best_t, S, P.max_depth)) break;  // absorbed or depth exhausted: black
-          }
-          L.pix.x += color.x;  // render.nim:67
-          L.pix.y += color.y;
-          L.pix.z += color.z;
-        }
-        if (lane == 0) {
-          double* out = P.pixels + 3ull * pid;  // the sum; draw_kernel applies canvas.nim:47-54 afterwards
-          out[0] = L.pix.x;
-          out[1] = L.pix.y;
-          out[2] = L.pix.z;
-        }
-        __syncwarp();
-      }
-    }
-    // An SM set aside for cooperative warps (CoopLayout mode 1): its other warps take no work until those are done.
-    if (role.coop_cta) asm volatile("bar.sync 1, %0;" ::"n"(BLOCK) : "memory");
-    if (role.deal_rank == 0xffffffffu) first_fetch = false;  // dealt nothing: straight to the queue
-  }
-
   for (;;) {
     // =================================================================== phase S
     if (active && trav_done) {
@@ -557,17 +638,17 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
       V3 color = v3(0, 0, 0);
       if (P.max_depth <= 0) {  // render.nim:25 — the bounce loop body never runs
         sample_done = true;
-      } else if (++seg_count, ++pix_seg, best_rec >= 0) {
-        const double2* __restrict__ r = recs + kRecStride16 * best_rec;
+      } else if (++seg_count, ++pix_seg, C.best_rec >= 0) {
+        const double2* __restrict__ r = recs + kRecStride16 * C.best_rec;
         const double2 a2 = r[2], a6 = r[6], a7 = r[7];
         const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
         Surface S;
-        S.center = rec_center(r, kind_mat, L.time, qc);  // moving_spheres.nim:61
+        S.center = rec_center(r, kind_mat, L.time, C.qc);  // moving_spheres.nim:61
         S.inv_r = a2.y;
         S.albedo = v3(a6.x, a6.y, a7.x);
         S.fuzz_or_ior = a7.y;
         S.mat_kind = (kind_mat >> 8) & 0xffu;
-        sample_done = shade_hit(L, best_t, S, P.max_depth);
+        sample_done = shade_hit(L, C.best_t, S, P.max_depth);
       } else {
         color = shade_miss(L);
         sample_done = true;
@@ -710,16 +791,16 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
           const int4 n3 = ld16i<(STAGE >= 1)>(nodes, nodes_sa, ni + 3);
           ++box_count;
           // child 0: lo = (n0.x, n0.y, n0.z), hi = (n0.w, n1.x, n1.y); child 1: lo = (n1.z, n1.w, n2.x), hi = (n2.y, n2.z, n2.w)
-          float ax0 = fmaf(n0.x, idx, -oix), ax1 = fmaf(n0.w, idx, -oix);
-          float ay0 = fmaf(n0.y, idy, -oiy), ay1 = fmaf(n1.x, idy, -oiy);
-          float az0 = fmaf(n0.z, idz, -oiz), az1 = fmaf(n1.y, idz, -oiz);
+          float ax0 = fmaf(n0.x, R.idx, -R.oix), ax1 = fmaf(n0.w, R.idx, -R.oix);
+          float ay0 = fmaf(n0.y, R.idy, -R.oiy), ay1 = fmaf(n1.x, R.idy, -R.oiy);
+          float az0 = fmaf(n0.z, R.idz, -R.oiz), az1 = fmaf(n1.y, R.idz, -R.oiz);
           float near0 = fmaxf(fmaxf(fminf(ax0, ax1), fminf(ay0, ay1)), fmaxf(fminf(az0, az1), 0.f));
-          float far0 = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), best_f));
-          float bx0 = fmaf(n1.z, idx, -oix), bx1 = fmaf(n2.y, idx, -oix);
-          float by0 = fmaf(n1.w, idy, -oiy), by1 = fmaf(n2.z, idy, -oiy);
-          float bz0 = fmaf(n2.x, idz, -oiz), bz1 = fmaf(n2.w, idz, -oiz);
+          float far0 = fminf(fminf(fmaxf(ax0, ax1), fmaxf(ay0, ay1)), fminf(fmaxf(az0, az1), C.best_f));
+          float bx0 = fmaf(n1.z, R.idx, -R.oix), bx1 = fmaf(n2.y, R.idx, -R.oix);
+          float by0 = fmaf(n1.w, R.idy, -R.oiy), by1 = fmaf(n2.z, R.idy, -R.oiy);
+          float bz0 = fmaf(n2.x, R.idz, -R.oiz), bz1 = fmaf(n2.w, R.idz, -R.oiz);
           float near1 = fmaxf(fmaxf(fminf(bx0, bx1), fminf(by0, by1)), fmaxf(fminf(bz0, bz1), 0.f));
-          float far1 = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), best_f));
+          float far1 = fminf(fminf(fmaxf(bx0, bx1), fmaxf(by0, by1)), fminf(fmaxf(bz0, bz1), C.best_f));
           const bool h0 = near0 <= far0, h1 = near1 <= far1;
           if (h0 && h1) {
             const bool first0 = near0 <= near1;
@@ -735,7 +816,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
             while (sp > 0) {
               --sp;
               const int2 e = stk[sp];
-              if (__int_as_float(e.y) <= best_f) {
+              if (__int_as_float(e.y) <= C.best_f) {
                 cur = e.x;
                 trav_done = false;
                 break;
@@ -762,7 +843,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
         while (sp > 0) {
           --sp;
           const int2 e = stk[sp];
-          if (__int_as_float(e.y) <= best_f) {
+          if (__int_as_float(e.y) <= C.best_f) {
             cur = e.x;
             trav_done = false;
             break;
