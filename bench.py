@@ -1,21 +1,27 @@
 #!/usr/bin/env python
 """bench.py — Mray/s of the render path on BASELINE.json's workload (config C2: book-1 random_scene,
-1200x675, 500 spp, depth 50).
+1200x675, 500 spp, depth 50), and with --workload on the other configurations (c1, c4 animation, c5 stress).
 
   python bench.py --gpus N --steps K --warmup W            our sm_100a path (N>1: under torchrun, NCCL)
   python bench.py --impl reference --gpus N ...             the reference's CPU algorithm on the host cores
 
-One "step" = one full render of the workload (rows interleaved over the N ranks + one all_gather).
-`value`   : primary rays / CUDA-event time, scene already resident in HBM, image left in HBM.
+One "step" = one full render of the workload (rows interleaved over the N ranks + one gather to rank 0; for the
+animation c4: all 300 frames, frame f on rank f mod N, + one gather of the RGB8 frames).
+`value`   : primary rays / CUDA-event time, scene already resident in HBM, image left in rank 0's HBM.
 `e2e`     : the same metric through the public host-buffer call (tor_render for N=1; DistributedRenderer.render
             for N>1): scene packing + H2D, kernel, gather, D2H into the caller's canvas, every step.
-`roofline`: algorithmic HBM bytes of the render kernel / its CUDA-event time against the measured copy peak
-            (MEASURED_PEAKS.json) — tiny by construction: the kernel is FP64-issue bound, so the
-            binding roof is reported beside it under roofline.fp64.
+`roofline`: the binding roof of this path is the FP64 pipe: FP64 arithmetic instructions the step
+            executes (per-opcode counts of the committed ncu capture of the same launch, profiles/fp64_ops.json)
+            / device time, against the DFMA issue rate measured on the same GPU in the same run.  The HBM roofline the
+            metric's wording asks for (algorithmic bytes / time against MEASURED_PEAKS.json) is kept beside it under
+            roofline.hbm — it is ~1e-5 by construction (a megakernel writes the framebuffer once).
+`image_check`: sha256 of the image that arrived on rank 0 against the CPU oracle's digest of the full frame
+            (tests/golden/c2_oracle_digest.json) — at every GPU count the same bits.
 `cpu_baseline`: the oracle (C++ restatement of the reference, glibc libm, OpenMP over all host cores) timed on
             a bounded row sample of the same workload.  The Nim/Weave binary cannot be built (no nim).
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -30,11 +36,37 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (nrows, ncols, spp, max_depth, scene half-grid)
-    "c1": (216, 384, 100, 50, 11),   # trace_of_radiance.nim:27-32
-    "c2": (675, 1200, 500, 50, 11),  # BASELINE.json configs[1]
+    "c1": (216, 384, 100, 50, 11),     # trace_of_radiance.nim:27-32
+    "c2": (675, 1200, 500, 50, 11),    # BASELINE.json configs[1] (and [2] at N = 8)
+    "c5": (2160, 3840, 2000, 50, 50),  # BASELINE.json configs[4]: 10 002 spheres (random_scene grid -50 ..< 50)
 }
+ANIMATION = {"c4": dict(nrows=144, ncols=256, spp=100, depth=50, t_max=9.0, skip=6, frames=300)}  # configs[3]
 GAMMA = 2.2
-METRIC = "Mray/s (primary rays) at 1200x675 / 500 spp random_scene"
+METRICS = {
+    "c1": "Mray/s (primary rays) at 384x216 / 100 spp random_scene",
+    "c2": "Mray/s (primary rays) at 1200x675 / 500 spp random_scene",
+    "c5": "Mray/s (primary rays) at 3840x2160 / 2000 spp, 10 002 spheres",
+    "c4": "Mray/s (primary rays) over 300 frames of scenes_animated at 256x144 / 100 spp",
+}
+GOLDEN = {"c1": ("c1_oracle_digest.json", lambda d: d["det"]["f64_sha256"]),
+          "c2": ("c2_oracle_digest.json", lambda d: d["f64_sha256"])}
+
+
+def golden_digest(workload):
+    if workload not in GOLDEN:
+        return None
+    name, get = GOLDEN[workload]
+    p = os.path.join(ROOT, "tests", "golden", name)
+    return get(json.load(open(p))) if os.path.exists(p) else None
+
+
+def fp64_ops(workload, mode):
+    """FP64 arithmetic thread-instructions of one step on ONE GPU (render launches incl. the cost pre-pass), from the
+    committed ncu per-opcode capture (profiles/fp64_ops.json, tools/ncu_fp64_ops.py); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "fp64_ops.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(f"{workload}:{mode}")
+    return None
 
 
 def ncu_traffic(kernel):
@@ -161,7 +193,12 @@ def cpu_baseline(wl, target_s):
 
 
 def run_reference(args, wl, rank):
-    """--impl reference: the reference's CPU algorithm (oracle port) on this box's host cores."""
+    """--impl reference: the reference's CPU algorithm (oracle port) on this box's host cores.
+
+    Same config as our arm: the FIRST timed step renders the whole frame (every row) when the probe says that fits
+    the budget (--ref-full-seconds, default 240 s: C2 takes ~150-190 s on 16 threads); the remaining steps and the
+    warm-up render an evenly spread row sample of a few seconds each, so that the driver's --steps K run still ends in
+    minutes.  The value is all timed rays / all timed seconds."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -170,30 +207,47 @@ def run_reference(args, wl, rank):
     nrows, ncols, spp, depth, half = wl
     world = O.random_scene(0xFACADE, half)
     cam = O.book_camera(16.0 / 9.0)
-    per_step = max(2.0, min(15.0, 150.0 / max(1, args.steps + args.warmup)))
     probe = cpu_sample_rows(nrows, 3)
     t_probe = oracle_time_rows(O, wl, probe, cam, world)
-    n = int(max(1, min(nrows, per_step / (t_probe / len(probe)))))
+    per_row = t_probe / len(probe)
+    est_full = per_row * nrows
+    full_first = est_full <= args.ref_full_seconds
+    per_step = max(2.0, min(15.0, 60.0 / max(1, args.steps + args.warmup)))
+    n = int(max(1, min(nrows, per_step / per_row)))
     rows = cpu_sample_rows(nrows, n)
     for _ in range(args.warmup):
         oracle_time_rows(O, wl, rows, cam, world)
-    times = [oracle_time_rows(O, wl, rows, cam, world) for _ in range(args.steps)]
-    rays = len(rows) * ncols * spp
+    times, rays = [], 0
+    for k in range(args.steps):
+        sel = list(range(nrows)) if (full_first and k == 0) else rows
+        times.append(oracle_time_rows(O, wl, sel, cam, world))
+        rays += len(sel) * ncols * spp
     total = sum(times)
-    value = rays * args.steps / total / 1e6
-    sample = (f"each step = {len(rows)} of {nrows} rows evenly spread ({rays / 1e6:.1f} M primary rays) of the same "
-              "workload; C++/OpenMP restatement of render.nim (oracle/), glibc libm, all host threads")
+    value = rays / total / 1e6
+    if full_first:
+        sample = (f"step 1 = the whole frame ({nrows} rows, {nrows * ncols * spp / 1e6:.0f} M primary rays, "
+                  f"{times[0]:.1f} s); steps 2..{args.steps} = {len(rows)} of {nrows} rows evenly spread each; ")
+    else:
+        sample = (f"each step = {len(rows)} of {nrows} rows evenly spread ({len(rows) * ncols * spp / 1e6:.1f} M primary "
+                  f"rays): a whole frame would take ~{est_full:.0f} s on these cores; ")
+    sample += "C++/OpenMP restatement of render.nim (oracle/), glibc libm, all host threads"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mray/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRICS[args.workload], "value": value, "unit": "Mray/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: random_scene(seed 0xFACADE) {ncols}x{nrows} / {spp} spp / depth {depth}",
-                   "sample": sample},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, wl, len(world)), "sample": sample,
+                   "full_frame_in_step_1": full_first},
         "cpu_baseline": {"value": value, "unit": "Mray/s", "cores": host_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mray/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), file=RESULT_OUT, flush=True)
+
+
+def workload_name(name, wl, n_obj):
+    nrows, ncols, spp, depth, half = wl
+    return (f"{name}: random_scene(seed 0xFACADE, grid -{half}..<{half}, {n_obj} objects) {ncols}x{nrows} / {spp} spp / "
+            f"depth {depth}, gamma float32(2.2)")
 
 
 # ---------------------------------------------------------------------------------- our arm
@@ -236,40 +290,77 @@ def _run_ours_on_stream(args, wl, rank, world_size, local_rank, dev, torch, dist
     if args.mode == "fast":
         route |= T.api.TOR_MODE_FAST
 
-    def step():
-        return R.render_device(nrows, ncols, spp, GAMMA, depth, flags=route)
+    def step(flags=route):
+        return R.render_device(nrows, ncols, spp, GAMMA, depth, flags=flags)
+
+    def timed_steps(flags):
+        """K steps, device time per step (CUDA events on the launching stream), L2 flushed between them.  Returns
+        (sum of step times in ms, max over ranks; sum of render-kernel times in ms, max over ranks; wall seconds)."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        kernel_ms = []
+        barrier()
+        t_wall = time.perf_counter()
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            step(flags)
+            b.record()
+            b.synchronize()
+            kernel_ms.append(ctx.last_kernel_ms())
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev), sum(kernel_ms)], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), t_wall, statistics.mean(kernel_ms)
 
     for _ in range(max(3, args.warmup) if args.warmup >= 0 else 0):
         step()
     barrier()
 
-    # ---- timed region: K steps, device time per step (CUDA events on the launching stream), L2 flushed between
+    # ---- timed region
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ctx.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms = []
-    barrier()
-    t_wall = time.perf_counter()
-    for a, b in ev:
-        flush.zero_()
-        a.record()
-        step()
-        b.record()
-        b.synchronize()
-        kernel_ms.append(ctx.last_kernel_ms())
-    barrier()
-    t_wall = time.perf_counter() - t_wall
+    dev_ms, kern_ms, t_wall, my_kernel_ms = timed_steps(route)
     clocks = sampler.stop() if sampler else None
     launches = ctx.launch_count() - launches0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([dev_ms, sum(kernel_ms)], dtype=torch.float64, device=dev)
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, kern_ms = float(t[0]), float(t[1])
+    sched = ctx.last_schedule() if args.mode == "exact" and args.route == "bvh" else None
     if dev_ms < 0.98 * kern_ms:
         raise SystemExit(f"timing events ({dev_ms:.3f} ms) do not bracket the render kernel ({kern_ms:.3f} ms)")
     rays_per_step = nrows * ncols * spp
     value = rays_per_step * args.steps / (dev_ms * 1e-3) / 1e6
+
+    # ---- image check: what arrived on rank 0 in the last timed step, bit for bit
+    image_check = None
+    slots = step()
+    torch.cuda.synchronize(dev)
+    if rank == 0:
+        img = R.image(slots, nrows).cpu().numpy()
+        digest = hashlib.sha256(img.tobytes()).hexdigest()
+        want = golden_digest(args.workload) if args.mode == "exact" else None
+        image_check = {"sha256": digest, "finite": bool(np.isfinite(img).all())}
+        if want is not None:
+            image_check["oracle_sha256"] = want
+            image_check["result"] = "ok" if digest == want else "MISMATCH"
+            image_check["against"] = f"tests/golden/{GOLDEN[args.workload][0]} (CPU oracle, full frame)"
+        else:
+            image_check["result"] = "no committed digest for this workload / mode"
+        del img
+    if world_size > 1:  # independent of any golden file: rank 0 renders a few rows alone and compares
+        rows = sorted(set(int((i + 0.5) * nrows / 5) for i in range(5)))
+        if rank == 0:
+            mine = torch.zeros((len(rows), ncols, 3), dtype=torch.float64, device=dev)
+            for k, r in enumerate(rows):
+                ctx.render_device_async(mine[k].data_ptr(), nrows, ncols, spp, GAMMA, depth, route, rows=(r, r + 1, 1),
+                                        stream=torch.cuda.current_stream(dev).cuda_stream)
+            torch.cuda.synchronize(dev)
+            full = R.image(slots, nrows)
+            same = all(torch.equal(full[r], mine[k]) for k, r in enumerate(rows))
+            image_check["gathered_rows_equal_single_rank_render"] = bool(same)
+            image_check["rows_checked"] = rows
+            if not same:
+                image_check["result"] = "MISMATCH"
+        barrier()
 
     # ---- e2e: host buffers through the public call, every step: pack + H2D + render (+ gather) + D2H
     pinned = torch.empty((nrows, ncols, 3), dtype=torch.float64, pin_memory=True)
@@ -277,130 +368,132 @@ def _run_ours_on_stream(args, wl, rank, world_size, local_rank, dev, torch, dist
     canvas.pixels = pinned.numpy()
     e2e_steps = max(1, min(args.steps, 3))
 
-    def e2e_step():
+    def e2e_step(flags=route):
         if world_size == 1:
-            ctx.render(canvas, cam, scene, depth, flags=route)  # tor_render: the drop-in for render.nim:49
+            ctx.render(canvas, cam, scene, depth, flags=flags)  # tor_render: the drop-in for render.nim:49
         else:
-            R.render(canvas, cam, scene, depth, flags=route)
+            R.render(canvas, cam, scene, depth, flags=flags)
 
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world_size > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = rays_per_step * e2e_steps / float(te[0]) / 1e6
-    h2d = int(scene.objects.nbytes) + 192  # what the caller hands over; the packed blob on the wire is reported below
-    d2h = nrows * ncols * 24
+    def timed_e2e(flags):
+        e2e_step(flags)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step(flags)
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return rays_per_step * e2e_steps / float(te[0]) / 1e6
 
-    # ---- roofline of the render kernel (the only kernel of ours in the step)
+    e2e_value = timed_e2e(route)
+    if rank == 0 and image_check is not None and image_check.get("oracle_sha256"):
+        image_check["e2e_canvas_matches"] = hashlib.sha256(canvas.pixels.tobytes()).hexdigest() == image_check["oracle_sha256"]
+    h2d = int(scene.objects.nbytes) + 192  # what the caller hands over (every rank, for N > 1)
+    d2h = nrows * ncols * 24               # rank 0 only
+
+    # ---- rooflines of the render kernel (the only kernel of ours that matters in the step)
     hbm_peak, peak_src = peaks()
     my_rows = D.partition_rows(nrows, rank, world_size)[1]
     alg_bytes = my_rows * ncols * 24 + len(scene) * 112 + 192  # framebuffer write + scene + camera
-    kern_s = (kernel_ms and statistics.mean(kernel_ms) or 0.0) * 1e-3
-    achieved = alg_bytes / kern_s / 1e9
-    # ALU side: counted once (instrumented, untimed) — segments are deterministic
-    R.render_device(nrows, ncols, spp, GAMMA, depth, flags=T.api.TOR_FLAG_COUNT_SEGMENTS | route)
+    kern_s = my_kernel_ms * 1e-3
+    hbm_achieved = alg_bytes / kern_s / 1e9
+    # ALU side: work counters (instrumented, untimed) — segments are deterministic
+    step(T.api.TOR_FLAG_COUNT_SEGMENTS | route)
     torch.cuda.synchronize(dev)
     cnt = ctx.counters()
-    ct = torch.tensor([cnt["primary_rays"], cnt["segments"]], dtype=torch.float64, device=dev)
+    ct = torch.tensor([cnt["primary_rays"], cnt["segments"], cnt["bvh_node_visits"], cnt["bvh_sphere_tests"]],
+                      dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(ct, op=dist.ReduceOp.SUM)
     segments = float(ct[1])
     fp64_peak = ctx.measure_fp64_peak() if rank == 0 else 0.0
     n_obj = len(scene)
-    tests_per_s = segments * n_obj / (dev_ms / args.steps * 1e-3)
+    ops = fp64_ops(args.workload, args.mode if args.route == "bvh" else "brute")
 
     # ---- split-stream mode (TOR_MODE_FAST) beside the headline: same workload, same float64 arithmetic, the pixel's
     #      sample loop cut into RNG substreams (deterministic, bit-exact against the oracle's restatement, a different
     #      Monte-Carlo estimate than the reference's image) — reported, never substituted for `value`
     split = None
-    if args.mode == "exact" and args.route == "bvh":
+    if args.mode == "exact" and args.route == "bvh" and not args.no_split_stream:
         fl = route | T.api.TOR_MODE_FAST
         for _ in range(2):
-            R.render_device(nrows, ncols, spp, GAMMA, depth, flags=fl)
-        barrier()
-        fev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for a, b in fev:
-            flush.zero_()
-            a.record()
-            R.render_device(nrows, ncols, spp, GAMMA, depth, flags=fl)
-            b.record()
-            b.synchronize()
-        barrier()
-        ft = torch.tensor([sum(a.elapsed_time(b) for a, b in fev)], dtype=torch.float64, device=dev)
-        if world_size > 1:
-            dist.all_reduce(ft, op=dist.ReduceOp.MAX)
-        fms = float(ft[0]) / args.steps
-        # the same through the host-buffer call
-        def fast_e2e_step():
-            if world_size == 1:
-                ctx.render(canvas, cam, scene, depth, flags=fl)
-            else:
-                R.render(canvas, cam, scene, depth, flags=fl)
-
-        fast_e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            fast_e2e_step()
-        barrier()
-        tf = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world_size > 1:
-            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            step(fl)
+        f_dev_ms, _, _, f_kernel_ms = timed_steps(fl)
+        fms = f_dev_ms / args.steps
+        f_e2e = timed_e2e(fl)
         # algorithmic HBM bytes of the split-stream step: the exact mode's + one 24-byte partial sum per (pixel, range)
         # written by the render kernel and read by substream_reduce_kernel
         nsub = T.api.fast_substream_count(fl, nrows, ncols, spp)
         split_bytes = alg_bytes + 2 * 24 * my_rows * ncols * nsub
         split = {"value": rays_per_step / (fms * 1e-3) / 1e6, "unit": "Mray/s", "ms_per_step": fms,
                  "substreams_per_pixel": nsub,
-                 "roofline": {"bound": "hbm", "achieved": split_bytes / (fms * 1e-3) / 1e9, "peak": hbm_peak,
-                              "unit": "GB/s", "frac": split_bytes / (fms * 1e-3) / 1e9 / hbm_peak,
-                              "algorithmic_bytes_per_step": split_bytes},
-                 "e2e": rays_per_step * e2e_steps / float(tf[0]) / 1e6, "ncu": ncu_pipe_summary("bvh_split"),
+                 "hbm": {"achieved": split_bytes / (f_kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": split_bytes / (f_kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                         "algorithmic_bytes_per_launch": split_bytes},
+                 "e2e": f_e2e,
                  "flags": "TOR_MODE_FAST (automatic substream count: 2^24 / pixels, <= spp, <= 32)",
                  "parity": "bit-exact vs the oracle's render_split; vs the reference image: within 4*sqrt(2)*sigma/"
                            "sqrt(spp) per pixel (tests/test_split_stream.py)"}
+        sops = fp64_ops(args.workload, "fast")
+        if sops and rank == 0 and fp64_peak > 0:
+            ach = sops["fp64_arith_thread_inst"] / world_size / (f_kernel_ms * 1e-3)
+            split["roofline"] = {"bound": "fp64", "achieved": ach / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                                 "frac": ach / fp64_peak, "source": sops.get("source")}
 
     if rank == 0:
         base = cpu_baseline(wl, args.cpu_seconds) if (world_size == 1 and not args.no_cpu_baseline) else None
+        roof = {"kernel": "render_bvh_kernel" if args.route == "bvh" else "render_exact_kernel",
+                "kernel_ms": my_kernel_ms,
+                "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": hbm_achieved / hbm_peak, "peak_source": peak_src,
+                        "traffic": (ncu_traffic("render_bvh_kernel" if args.route == "bvh" else "render_exact_kernel")
+                                    if args.workload == "c2" and world_size == 1 else None),
+                        "algorithmic_bytes_per_launch": alg_bytes,
+                        "note": "megakernel: HBM sees the framebuffer write + one scene read per CTA (from L2)"},
+                "work": {"segments_per_step": segments, "bvh_node_visits_per_step": float(ct[2]),
+                         "sphere_tests_per_step": float(ct[3]), "route": args.route,
+                         "full_scan_sphere_tests_avoided_per_step": max(0.0, segments * n_obj - float(ct[3]))}}
+        if ops and fp64_peak > 0:
+            # the capture is of ONE GPU rendering the whole frame; N ranks split the same instructions (the image and
+            # every path in it are identical), up to the pre-pass's fixed 8 samples per pixel
+            per_rank = ops["fp64_arith_thread_inst"] / world_size
+            ach = per_rank / kern_s
+            roof.update({"bound": "fp64", "achieved": ach / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                         "frac": ach / fp64_peak,
+                         "definition": "FP64 arithmetic instructions executed per second, lane level (DADD + DMUL + DFMA, "
+                                       "one operation each: the reference's arithmetic is non-fused, -fmad=false), "
+                                       "against the DFMA issue rate measured on this GPU in this run "
+                                       "(tor_measure_fp64_peak)",
+                         "fp64_arith_thread_inst_per_step": ops["fp64_arith_thread_inst"], "per_opcode": ops.get("per_opcode"),
+                         "source": ops.get("source"), "traffic": roof["hbm"]["traffic"]})
+        else:
+            roof.update({"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": hbm_achieved / hbm_peak, "traffic": roof["hbm"]["traffic"],
+                         "note": "no FP64 instruction capture committed for this workload / mode (profiles/fp64_ops.json): "
+                                 "only the HBM roofline can be stated, and it is not the binding one",
+                         "measured_dfma_per_s": fp64_peak})
         line = {
-            "metric": METRIC, "value": value, "unit": "Mray/s", "n_gpus": world_size, "steps": args.steps,
+            "metric": METRICS[args.workload], "value": value, "unit": "Mray/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: random_scene(seed 0xFACADE, {n_obj} objects) {ncols}x{nrows} / "
-                                   f"{spp} spp / depth {depth}, gamma float32(2.2), " +
+            "config": {"workload": workload_name(args.workload, wl, n_obj) + ", " +
                                    ("exact mode (bit-identical image)" if args.mode == "exact" else
                                     "split-stream mode (TOR_MODE_FAST)"),
-                       "partition": f"rows interleaved over {world_size} rank(s) + one all_gather",
+                       "partition": f"rows interleaved over {world_size} rank(s)" +
+                                    (" + one gather to rank 0 (NCCL send/recv)" if world_size > 1 else ""),
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)",
                        "wall_s_timed_region": t_wall},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mray/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "call": "tor_render (host canvas, pinned)" if world_size == 1 else
-                    "DistributedRenderer.render (scene upload + kernel + all_gather + D2H)"},
+                    "DistributedRenderer.render (scene upload + kernel + gather to rank 0 + strided D2H on rank 0)"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak,
-                         "traffic": (ncu_traffic("render_bvh_kernel" if args.route == "bvh" else "render_exact_kernel")
-                                     if args.workload == "c2" and world_size == 1 else None),
-                         "peak_source": peak_src,
-                         "kernel": "render_bvh_kernel" if args.route == "bvh" else "render_exact_kernel", "kernel_ms": statistics.mean(kernel_ms),
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "megakernel: HBM sees only the framebuffer write + one scene read; the binding roof is "
-                                 "FP64 issue, see fp64",
-                         "fp64": {"segments_per_step": segments, "sphere_tests_per_s": tests_per_s,
-                                  "measured_dfma_per_s": fp64_peak, "route": args.route,
-                                  "bvh_node_visits_per_step": cnt.get("bvh_node_visits"),
-                                  "bvh_sphere_tests_per_step": cnt.get("bvh_sphere_tests"),
-                                  "ncu": ncu_pipe_summary() if args.route == "bvh" else None,
-                                  "reference_flop_per_test": 32.8,
-                                  "reference_equivalent_flop_per_s": tests_per_s * 32.8}},
+            "image_check": image_check,
+            "roofline": roof,
         }
+        if sched:
+            line["schedule"] = sched
         if split:
             line["split_stream_mode"] = split
         if base:
@@ -428,7 +521,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + sorted(ANIMATION))
     ap.add_argument("--route", default="bvh", choices=["bvh", "brute"],
                     help="closest-hit search: BVH in front of the reference's sphere test (default) or the full scan")
     ap.add_argument("--mode", default="exact", choices=["exact", "fast"],
@@ -436,11 +529,21 @@ def main():
                          "TOR_MODE_FAST split-stream mode as the measured arm")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-split-stream", action="store_true", help="skip the split_stream_mode leg")
+    ap.add_argument("--in-flight", type=int, default=4, help="c4: animation frames enqueued at once per GPU")
+    ap.add_argument("--ref-full-seconds", type=float, default=240.0,
+                    help="--impl reference renders the whole frame in its first step when the probe predicts at most "
+                         "this many seconds")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload in ANIMATION:
+        import bench_animation
+
+        bench_animation.main(args, ANIMATION[args.workload], METRICS[args.workload], RESULT_OUT)
+        return
+    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl, rank)
         return

@@ -38,6 +38,13 @@ def _worker(rank, world, port, nrows, ncols, spp, q):
         local = torch.zeros((rpr, ncols, 3), dtype=torch.float64)
         local[:n] = torch.from_numpy(full[rows[0]:rows[1]:rows[2]])
         img = D.gather_rows(local, nrows)
+        # the single-receiver form used by DistributedRenderer: rank 0 gets the slots, nobody else gets anything
+        slots = D.gather_rows_to(local, nrows, dst=0)
+        assert (slots is None) == (rank != 0)
+        if rank == 0:
+            canvas = np.zeros((nrows, ncols, 3))
+            D.scatter_slots_to_canvas(slots.numpy(), canvas)
+            assert canvas.tobytes() == img.numpy().tobytes()
         q.put((rank, img.numpy().tobytes()))
     finally:
         dist.destroy_process_group()

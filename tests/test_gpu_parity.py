@@ -402,3 +402,49 @@ def test_cooperative_pixels_default_policy_on_a_gpu_share_of_c2(tor, oracle, gpu
     ref = np.zeros((h, w, 3))
     oracle.render(h, w, spp, cam.as_array(), world.objects, rows=(203, 204, 1), math="det", out=ref)
     assert a.pixels[203].tobytes() == ref[203].tobytes()
+
+
+# ---------------------------------------------------------------------------------- device-resident animation
+def test_device_animation_frames_equal_the_oracle(tor, oracle, gpu_ctx):
+    """tor_animation_dev_*: physics, record rebuild and BVH re-fit on the device (no per-frame H2D).  Every frame
+    equals the oracle's render of the oracle's own scene iterator, including frames late in the animation (spheres
+    high above the ground: the re-fitted boxes must still contain them) and frames that are only stepped."""
+    an = tor.DeviceAnimation(gpu_ctx, height=27, width=48, t_max=9.0, in_flight=3)
+    frames = {}
+    n, ms = an.render_all(samples_per_pixel=4, on_frame=lambda i, rgb: frames.__setitem__(i, rgb.copy()), max_frames=9)
+    assert n == 9 and sorted(frames) == list(range(9)) and ms > 0
+    ref = oracle.Animation(height=27, width=48, t_max=9.0)
+    for i in range(9):
+        cam_arr, objs = ref.next_frame(skip=6)
+        want = oracle.quantise_rgb8(oracle.render(27, 48, 4, cam_arr, objs, math="det"))
+        assert np.array_equal(frames[i], want), i
+    an.close()
+    # every 20th frame of the whole animation on "rank 1 of 20": 285 frames are physics-only steps in between
+    an = tor.DeviceAnimation(gpu_ctx, height=18, width=32, t_max=9.0, in_flight=2)
+    frames = {}
+    n, _ = an.render_all(samples_per_pixel=3, on_frame=lambda i, rgb: frames.__setitem__(i, rgb.copy()), rank=1, world=20)
+    assert n == 300 and sorted(frames) == list(range(1, 300, 20))
+    ref = oracle.Animation(height=18, width=32, t_max=9.0)
+    for i in range(300):
+        got = ref.next_frame(skip=6)
+        assert got is not None
+        if i in frames:
+            want = oracle.quantise_rgb8(oracle.render(18, 32, 3, got[0], got[1], math="det"))
+            assert np.array_equal(frames[i], want), i
+    an.close()
+
+
+def test_device_animation_split_stream_equals_host_pipeline(tor, gpu_ctx):
+    """The same frames through the host iterator (scene re-packed and BVH rebuilt per frame) and through the device
+    pipeline (re-fitted boxes), in split-stream mode: identical bytes — the hierarchy is only a filter."""
+    fl = tor.api.TOR_MODE_FAST
+    a = {}
+    tor.render_animation(tor.Animation(height=36, width=64, t_max=9.0), samples_per_pixel=8, in_flight=2, flags=fl,
+                         on_frame=lambda i, rgb: a.__setitem__(i, rgb.copy()), max_frames=6)
+    b = {}
+    an = tor.DeviceAnimation(gpu_ctx, height=36, width=64, t_max=9.0, in_flight=2)
+    an.render_all(samples_per_pixel=8, flags=fl, on_frame=lambda i, rgb: b.__setitem__(i, rgb.copy()), max_frames=6)
+    an.close()
+    assert sorted(a) == sorted(b) == list(range(6))
+    for i in range(6):
+        assert np.array_equal(a[i], b[i]), i

@@ -8,6 +8,7 @@ sm_100a library and a CUDA device.
 """
 from .api import (  # noqa: F401
     Animation,
+    DeviceAnimation,
     PinnedBuffer,
     H264Encoder,
     MP4Muxer,

@@ -57,7 +57,8 @@ EXPORTED_SYMBOLS = [
     "tor_launch_count", "tor_measure_fp64_peak", "tor_get_traversal_counters", "tor_scene_info", "tor_camera_make", "tor_random_scene", "tor_export_ppm", "tor_quantise_rgb8", "tor_animation_create",
     "tor_animation_next_frame", "tor_animation_destroy", "tor_render_rgb8", "tor_render_rgb8_async", "tor_host_alloc",
     "tor_host_free", "tor_render_ycbcr420", "tor_render_ycbcr420_async", "tor_h264_open", "tor_h264_frame_buffer",
-    "tor_h264_flush_frame", "tor_h264_finish", "tor_mp4_mux_h264_file", "tor_fast_substream_count", "tor_last_schedule",
+    "tor_h264_flush_frame", "tor_h264_finish", "tor_mp4_mux_h264_file", "tor_fast_substream_count", "tor_last_schedule", "tor_download_rows_async", "tor_animation_dev_create",
+    "tor_animation_dev_next", "tor_animation_dev_sync", "tor_animation_dev_launch_count", "tor_animation_dev_destroy",
 ]
 
 
@@ -125,6 +126,7 @@ def load_library():
     L.tor_render_device_async.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int64, C.c_uint32,
                                           C.c_int32, C.c_int32, C.c_int32, vp]
     L.tor_sync.argtypes = [vp]
+    L.tor_download_rows_async.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     L.tor_get_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.tor_get_traversal_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.tor_scene_info.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -143,6 +145,14 @@ def load_library():
     L.tor_animation_next_frame.restype = C.c_int64
     L.tor_animation_destroy.argtypes = [vp]
     L.tor_animation_destroy.restype = None
+    L.tor_animation_dev_create.argtypes = [vp, C.c_uint64, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32,
+                                           C.c_int32, C.POINTER(vp)]
+    L.tor_animation_dev_next.argtypes = [vp, C.c_int32, C.c_float, C.c_int64, C.c_uint32, vp, C.POINTER(C.c_int64)]
+    L.tor_animation_dev_sync.argtypes = [vp, C.POINTER(C.c_float)]
+    L.tor_animation_dev_launch_count.argtypes = [vp]
+    L.tor_animation_dev_launch_count.restype = C.c_int64
+    L.tor_animation_dev_destroy.argtypes = [vp]
+    L.tor_animation_dev_destroy.restype = None
     L.tor_export_ppm.argtypes = [C.POINTER(_CCanvas), C.c_char_p]
     L.tor_quantise_rgb8.argtypes = [C.POINTER(_CCanvas), C.POINTER(C.c_uint8)]
     _lib = L
@@ -409,6 +419,13 @@ class Context:
         self._check(self.L.tor_render_device_async(self.h, d_pixels_ptr, nrows, ncols, spp, float(np.float32(gamma)),
                                                    max_depth, flags, rb, re, rs, stream))
 
+    def download_rows_async(self, d_rows_ptr, host_pixels, ncols, row_begin, row_step, nsel, stream=None):
+        """Compact device rows -> rows row_begin, row_begin + row_step, ... of the host canvas array (one strided copy)."""
+        if stream is not None and int(stream) == 0:
+            stream = 1  # cudaStreamLegacy
+        self._check(self.L.tor_download_rows_async(self.h, d_rows_ptr, host_pixels.ctypes.data, ncols, row_begin, row_step,
+                                                   nsel, stream))
+
     def sync(self):
         self._check(self.L.tor_sync(self.h))
 
@@ -612,6 +629,98 @@ def render_animation(animation, samples_per_pixel=100, max_depth=50, gamma_corre
     for c in ctxs:
         c.close()
     return n
+
+
+class DeviceAnimation:
+    """The animation with physics, scene rebuild and BVH re-fit on the device (tor_animation_dev_*): no per-frame
+    host-to-device copy.  Same frames, bit for bit, as `Animation` + `render_rgb8`.
+
+        an = DeviceAnimation(ctx, height=144, width=256, in_flight=4)
+        n = an.render_all(samples_per_pixel=100, on_frame=lambda i, rgb8: ...)
+    """
+
+    def __init__(self, ctx=None, seed=0xFACADE, height=144, width=256, dt=0.005, t_min=0.0, t_max=9.0, skip=6,
+                 in_flight=4):
+        self.ctx = ctx or default_context()
+        self.L = self.ctx.L
+        self.height, self.width, self.in_flight = int(height), int(width), int(in_flight)
+        self.h = C.c_void_p()
+        self.ctx._check(self.L.tor_animation_dev_create(self.ctx.h, seed, height, width, dt, t_min, t_max, skip, in_flight,
+                                                         C.byref(self.h)))
+        self.bufs = [PinnedBuffer((self.height, self.width, 3)) for _ in range(self.in_flight)]
+
+    def next(self, samples_per_pixel, max_depth=50, gamma_correction=2.2, flags=0, out=None, render=True):
+        """Enqueues the next frame.  Returns its index, or None when the iterator is exhausted.  render=False only
+        advances the physics (the frame belongs to another rank)."""
+        idx = C.c_int64(-1)
+        ptr = out.ctypes.data if (render and out is not None) else None
+        if render and out is None:
+            raise ValueError("render=True needs a (pinned) output array")
+        rc = self.L.tor_animation_dev_next(self.h, samples_per_pixel, float(np.float32(gamma_correction)), max_depth, flags,
+                                           ptr, C.byref(idx))
+        if rc < 0:
+            self.ctx._check(rc)
+        return int(idx.value) if rc == 1 else None
+
+    def sync(self):
+        """Completes every frame enqueued so far; returns the device time (ms) they took."""
+        ms = C.c_float()
+        self.ctx._check(self.L.tor_animation_dev_sync(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self):
+        return int(self.L.tor_animation_dev_launch_count(self.h)) + self.ctx.launch_count()
+
+    def render_all(self, samples_per_pixel=100, max_depth=50, gamma_correction=2.2, flags=0, on_frame=None, max_frames=None,
+                   rank=0, world=1, out=None):
+        """The frame loop of trace_of_radiance_animation.nim:173-199.  Frame f is rendered when f % world == rank (frame-
+        parallel ranks step the physics of every frame themselves).  on_frame(index, rgb8) is called in frame order;
+        `out` (optional, (frames_of_this_rank, h, w, 3) uint8 pinned array) receives the frames directly instead of the
+        rotating buffers.  Returns (frames seen, device ms)."""
+        pending = []  # (frame index, buffer index) in flight
+        n_mine = 0
+        total_ms = 0.0
+        f = 0
+        while max_frames is None or f < max_frames:
+            mine = f % world == rank
+            if mine:
+                if out is not None:
+                    buf = out[n_mine]
+                else:
+                    k = n_mine % self.in_flight
+                    if len(pending) == self.in_flight:  # the buffer is still owned by a frame in flight
+                        total_ms += self.sync()
+                        for (pf, pk) in pending:
+                            if on_frame:
+                                on_frame(pf, self.bufs[pk].array)
+                        pending = []
+                    buf = self.bufs[k].array
+                idx = self.next(samples_per_pixel, max_depth, gamma_correction, flags, out=buf)
+            else:
+                idx = self.next(samples_per_pixel, max_depth, gamma_correction, flags, render=False)
+            if idx is None:
+                break
+            if mine:
+                if out is None:
+                    pending.append((idx, n_mine % self.in_flight))
+                n_mine += 1
+            f += 1
+        total_ms += self.sync()
+        for (pf, pk) in pending:
+            if on_frame:
+                on_frame(pf, self.bufs[pk].array)
+        return f, total_ms
+
+    def close(self):
+        if self.h:
+            self.L.tor_animation_dev_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def animation_dims(animation):

@@ -12,8 +12,10 @@
 #include <vector>
 
 #include "../../include/tor_b200.h"
+#include "tor_anim.hpp"
 #include "tor_bvh.hpp"
 #include "tor_kernels.cuh"
+#include "tor_kernels_anim.cuh"
 #include "tor_kernels_bvh.cuh"
 #include "tor_scene_pack.hpp"
 
@@ -721,6 +723,22 @@ int tor_render_device_async(tor_ctx* ctx, double* d_pixels, int32_t nrows, int32
                      row_end, row_step, s, /*timed=*/true);
 }
 
+int tor_download_rows_async(tor_ctx* ctx, const double* d_rows, double* host_pixels, int32_t ncols, int32_t row_begin,
+                            int32_t row_step, int32_t nsel, void* cuda_stream) {
+  if (!ctx) return TOR_ERR_INVALID_ARG;
+  if (!d_rows || !host_pixels || ncols <= 0 || row_begin < 0 || row_step <= 0 || nsel < 0)
+    return fail(ctx, TOR_ERR_INVALID_ARG, "tor_download_rows_async: bad arguments");
+  if (nsel == 0) return TOR_OK;
+  DeviceState& d = ctx->devs[0];
+  TOR_CUDA(ctx, cudaSetDevice(d.dev));
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : d.stream;
+  const size_t row_bytes = (size_t)ncols * 3 * sizeof(double);
+  // compact device rows -> canvas rows row_begin, row_begin + row_step, ...: one strided copy, no staging buffer
+  TOR_CUDA(ctx, cudaMemcpy2DAsync(host_pixels + (size_t)row_begin * ncols * 3, (size_t)row_step * row_bytes, d_rows,
+                                  row_bytes, row_bytes, (size_t)nsel, cudaMemcpyDeviceToHost, s));
+  return TOR_OK;
+}
+
 int tor_sync(tor_ctx* ctx) {
   if (!ctx) return TOR_ERR_INVALID_ARG;
   for (DeviceState& d : ctx->devs) {
@@ -787,18 +805,13 @@ int tor_render_rows(tor_ctx* ctx, tor_canvas* canvas, const tor_camera* cam, con
   return tor_sync(ctx);
 }
 
-int tor_render_rgb8_async(tor_ctx* ctx, const tor_canvas* canvas, const tor_camera* cam, const void* objects,
-                          int64_t len, int64_t stride, int64_t max_depth, uint32_t flags, uint8_t* rgb8_out) {
-  if (!ctx) return TOR_ERR_INVALID_ARG;
-  if (!canvas || !rgb8_out) return fail(ctx, TOR_ERR_INVALID_ARG, "canvas or rgb8_out is NULL");
-  const int32_t nrows = canvas->nrows, ncols = canvas->ncols;
-  int rc = check_canvas_dims(ctx, nrows, ncols, canvas->samples_per_pixel, max_depth, 0, nrows, 1);
-  if (rc) return rc;
-  rc = set_scene(ctx, cam, objects, len, stride);
-  if (rc) return rc;
+// Render the uploaded scene on device d of ctx and deliver the packed RGB8 image (io/ppm.nim quantisation, PPM row
+// order) to rgb8_out (host) asynchronously on d.stream.
+static int enqueue_rgb8(tor_ctx* ctx, int32_t nrows, int32_t ncols, int32_t spp, float gamma, int64_t max_depth,
+                        uint32_t flags, uint8_t* rgb8_out) {
   DeviceState& d = ctx->devs[0];
   const size_t npix = (size_t)nrows * ncols;
-  rc = ensure_capacity(ctx, d, device_blob_bytes(ctx), npix * 3 * sizeof(double));
+  int rc = ensure_capacity(ctx, d, device_blob_bytes(ctx), npix * 3 * sizeof(double));
   if (rc) return rc;
   if (npix * 3 > d.rgb8_cap) {
     if (d.d_rgb8) cudaFree(d.d_rgb8);
@@ -809,14 +822,30 @@ int tor_render_rgb8_async(tor_ctx* ctx, const tor_canvas* canvas, const tor_came
   }
   rc = upload_scene_to(ctx, d);
   if (rc) return rc;
-  rc = launch_rows(ctx, d, d.d_pixels, nrows, ncols, canvas->samples_per_pixel, canvas->gamma_correction, max_depth,
-                   flags, 0, nrows, 1, d.stream, /*timed=*/true);
+  rc = launch_rows(ctx, d, d.d_pixels, nrows, ncols, spp, gamma, max_depth, flags, 0, nrows, 1, d.stream, /*timed=*/true);
   if (rc) return rc;
   tor::quantise_rgb8_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, d.stream>>>(d.d_pixels, nrows, ncols, d.d_rgb8);
   TOR_CUDA(ctx, cudaGetLastError());
   ctx->launches += 1;
-  TOR_CUDA(ctx, cudaMemcpyAsync(rgb8_out, d.d_rgb8, npix * 3, cudaMemcpyDeviceToHost, d.stream));
+  // rgb8_out may be host memory (the caller's frame buffer) or device memory (a frame-parallel rank collecting its
+  // frames for one gather): unified addressing tells the copy which
+  TOR_CUDA(ctx, cudaMemcpyAsync(rgb8_out, d.d_rgb8, npix * 3, cudaMemcpyDefault, d.stream));
+  // the copy reads d_rgb8 after launch_rows' own end-of-launch event: move the context's busy mark behind it
+  TOR_CUDA(ctx, cudaEventRecord(d.ev_busy, d.stream));
+  d.busy = true;
   return TOR_OK;
+}
+
+int tor_render_rgb8_async(tor_ctx* ctx, const tor_canvas* canvas, const tor_camera* cam, const void* objects,
+                          int64_t len, int64_t stride, int64_t max_depth, uint32_t flags, uint8_t* rgb8_out) {
+  if (!ctx) return TOR_ERR_INVALID_ARG;
+  if (!canvas || !rgb8_out) return fail(ctx, TOR_ERR_INVALID_ARG, "canvas or rgb8_out is NULL");
+  const int32_t nrows = canvas->nrows, ncols = canvas->ncols;
+  int rc = check_canvas_dims(ctx, nrows, ncols, canvas->samples_per_pixel, max_depth, 0, nrows, 1);
+  if (rc) return rc;
+  rc = set_scene(ctx, cam, objects, len, stride);
+  if (rc) return rc;
+  return enqueue_rgb8(ctx, nrows, ncols, canvas->samples_per_pixel, canvas->gamma_correction, max_depth, flags, rgb8_out);
 }
 
 int tor_render_ycbcr420_async(tor_ctx* ctx, const tor_canvas* canvas, const tor_camera* cam, const void* objects,
@@ -996,6 +1025,255 @@ int tor_measure_fp64_peak(tor_ctx* ctx, double* dfma_per_second) {
   cudaFree(sink);
   *dfma_per_second = best;
   return TOR_OK;
+}
+
+// ------------------------------------------------------------------------------- device-resident animation
+struct tor_animation_dev {
+  tor_ctx* parent = nullptr;
+  tor_anim::Animation* an = nullptr;
+  int32_t skip = 6;
+  std::vector<tor_ctx*> slots;  // one context (= stream + frame buffers + its own copy of the packed scene) per frame in flight
+  std::vector<cudaEvent_t> ev_ready;
+  cudaStream_t phys = nullptr;  // physics + refit kernels, in frame order
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  bool timing_open = false;
+  double *d_vel = nullptr, *d_pos = nullptr, *d_rest = nullptr, *d_rad = nullptr;
+  int32_t *d_rec_dyn = nullptr, *d_node_order = nullptr, *d_level_off = nullptr, *d_flag = nullptr;
+  float* d_node_y = nullptr;
+  int32_t n_dyn = 0, n_levels = 0;
+  double pad = 0.0, s_limit = 0.0;
+  int64_t frame = 0;     // frames produced or skipped so far
+  int64_t rendered = 0;  // frames rendered by this object
+  int dev = 0;
+};
+
+int tor_animation_dev_create(tor_ctx* ctx, uint64_t seed, int32_t height, int32_t width, float dt, float t_min,
+                             float t_max, int32_t skip, int32_t in_flight, tor_animation_dev** out) {
+  if (!ctx || !out) return TOR_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (height <= 0 || width <= 0 || skip < 0 || in_flight < 1 || in_flight > 64 || !(dt > 0.f))
+    return fail(ctx, TOR_ERR_INVALID_ARG, "tor_animation_dev_create: bad arguments");
+  tor_animation_dev* A = new tor_animation_dev();
+  A->parent = ctx;
+  A->skip = skip;
+  A->dev = ctx->devs[0].dev;
+  A->an = tor_anim::animation_create(seed, height, width, dt, t_min, t_max);
+  auto bail = [&](int code, const std::string& msg) {
+    tor_animation_dev_destroy(A);
+    return fail(ctx, code, msg);
+  };
+  // the first frame's scene (all moving spheres at their start height) fixes the packed layout and the tree topology
+  std::vector<tor_hittable> objs;
+  tor_anim::animation_scene(*A->an, &objs);
+  tor_camera cam;
+  tor_anim::animation_camera(*A->an, &cam);
+  tor::PackedBvh bvh;
+  std::string err;
+  if (!tor::pack_bvh(objs, cam, &bvh, &err)) return bail(TOR_ERR_INVALID_ARG, err);
+  const tor::BvhView& bv = bvh.view;
+  A->n_dyn = (int32_t)A->an->spheres.size();
+  // same padding as the builder used (tor_bvh.hpp: 2^-19 of the largest coordinate); recover S from s_limit's source
+  {
+    double S = 0.0;
+    for (int k = 0; k < 3; ++k) {
+      double v = fabs(cam.origin[k]) + fabs(cam.lens_radius) * (fabs(cam.u[k]) + fabs(cam.v[k]));
+      if (v > S) S = v;
+    }
+    for (const tor_hittable& h : objs)
+      for (int k = 0; k < 3; ++k) {
+        const double r = fabs(h.radius), e = r + 1e-9 * (fabs(h.center0[k]) + r);
+        const double lo = h.center0[k] - e, hi = h.center0[k] + e;
+        if (fabs(lo) < 1e30 && fabs(hi) < 1e30) S = std::max(S, std::max(fabs(lo), fabs(hi)));
+      }
+    A->pad = ldexp(S, -19);
+    A->s_limit = (double)bv.s_limit;
+  }
+  // per tree record: its moving sphere (objects are [ground, moving spheres..., three big spheres])
+  std::vector<int32_t> rec_dyn((size_t)std::max(1, bv.n_tree_objs), -1);
+  const tor::ObjRec* recs = (const tor::ObjRec*)(bvh.blob.data() + bv.off_objs);
+  for (int32_t j = 0; j < bv.n_tree_objs; ++j) {
+    const int64_t o = (int64_t)recs[j].orig - 1;
+    if (o >= 0 && o < A->n_dyn) rec_dyn[(size_t)j] = (int32_t)o;
+  }
+  for (int32_t j = bv.n_tree_objs; j < bv.n_objects; ++j) {
+    const int64_t o = (int64_t)recs[j].orig - 1;
+    if (o >= 0 && o < A->n_dyn) return bail(TOR_ERR_INVALID_ARG, "internal: a moving sphere sits outside the tree");
+  }
+  // inner nodes by height
+  const tor::BvhNode* nodes = (const tor::BvhNode*)(bvh.blob.data() + bv.off_nodes);
+  std::vector<int32_t> node_h((size_t)bv.n_nodes, 0);
+  int32_t max_h = 0;
+  for (int32_t i = bv.n_nodes - 1; i >= 0; --i) {  // children have larger indices than their parent
+    int32_t h = 0;
+    for (int32_t c : {nodes[i].child0, nodes[i].child1})
+      if (c >= 0) h = std::max(h, node_h[(size_t)c] + 1);
+    node_h[(size_t)i] = h;
+    max_h = std::max(max_h, h);
+  }
+  A->n_levels = max_h + 1;
+  std::vector<int32_t> level_off((size_t)A->n_levels + 1, 0), order((size_t)bv.n_nodes);
+  for (int32_t i = 0; i < bv.n_nodes; ++i) level_off[(size_t)node_h[(size_t)i] + 1]++;
+  for (int32_t l = 0; l < A->n_levels; ++l) level_off[(size_t)l + 1] += level_off[(size_t)l];
+  {
+    std::vector<int32_t> cur(level_off.begin(), level_off.end() - 1);
+    for (int32_t i = 0; i < bv.n_nodes; ++i) order[(size_t)cur[(size_t)node_h[(size_t)i]]++] = i;
+  }
+  std::vector<double> vel, pos, rest, rad;
+  for (const tor_anim::AnimSphere& sp : A->an->spheres) {
+    vel.push_back(sp.velocity);
+    pos.push_back(sp.pos_y);
+    rest.push_back(sp.coef_restitution);
+    rad.push_back(sp.radius);
+  }
+  cudaError_t e = cudaSetDevice(A->dev);
+  auto up = [&](auto** dptr, const auto& v) {
+    using T = typename std::remove_reference<decltype(v)>::type::value_type;
+    const size_t bytes = std::max<size_t>(1, v.size()) * sizeof(T);
+    if (e == cudaSuccess) e = cudaMalloc((void**)dptr, bytes);
+    if (e == cudaSuccess && !v.empty()) e = cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  };
+  up(&A->d_vel, vel);
+  up(&A->d_pos, pos);
+  up(&A->d_rest, rest);
+  up(&A->d_rad, rad);
+  up(&A->d_rec_dyn, rec_dyn);
+  up(&A->d_node_order, order);
+  up(&A->d_level_off, level_off);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&A->d_node_y, (size_t)bv.n_nodes * 2 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&A->d_flag, sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemset(A->d_flag, 0, sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&A->phys, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&A->ev_t0);
+  if (e == cudaSuccess) e = cudaEventCreate(&A->ev_t1);
+  if (e != cudaSuccess) return bail(TOR_ERR_CUDA, std::string("tor_animation_dev_create: ") + cudaGetErrorString(e));
+  for (int k = 0; k < in_flight; ++k) {
+    tor_ctx* c = nullptr;
+    int rc = tor_ctx_create(&A->dev, 1, &c);
+    if (rc) return bail(rc, tor_last_error(nullptr));
+    A->slots.push_back(c);
+    c->objs = objs;
+    c->bvh = bvh;
+    c->cam = cam;
+    c->have_scene = true;
+    rc = upload_scene_to(c, c->devs[0]);  // the only host-to-device copy of scene data: once per slot
+    if (rc) return bail(rc, c->err);
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail(TOR_ERR_CUDA, "cudaEventCreate");
+    A->ev_ready.push_back(ev);
+  }
+  *out = A;
+  return TOR_OK;
+}
+
+void tor_animation_dev_destroy(tor_animation_dev* A) {
+  if (!A) return;
+  cudaSetDevice(A->dev);
+  if (A->phys) cudaStreamSynchronize(A->phys);
+  for (tor_ctx* c : A->slots) tor_ctx_destroy(c);
+  for (cudaEvent_t ev : A->ev_ready) cudaEventDestroy(ev);
+  for (void* p : {(void*)A->d_vel, (void*)A->d_pos, (void*)A->d_rest, (void*)A->d_rad, (void*)A->d_rec_dyn,
+                  (void*)A->d_node_order, (void*)A->d_level_off, (void*)A->d_node_y, (void*)A->d_flag})
+    if (p) cudaFree(p);
+  if (A->ev_t0) cudaEventDestroy(A->ev_t0);
+  if (A->ev_t1) cudaEventDestroy(A->ev_t1);
+  if (A->phys) cudaStreamDestroy(A->phys);
+  delete A->an;
+  delete A;
+}
+
+int tor_animation_dev_next(tor_animation_dev* A, int32_t samples_per_pixel, float gamma_correction, int64_t max_depth,
+                           uint32_t flags, uint8_t* rgb8_out, int64_t* frame_index) {
+  if (!A) return TOR_ERR_INVALID_ARG;
+  tor_ctx* ctx = A->parent;
+  tor_anim::Animation& an = *A->an;
+  // the iterator of scenes_animated.nim:176-225: the clock and the camera angle advance on the host (two scalars),
+  // the spheres on the device
+  int32_t nsteps = 0;
+  if (!an.started) {
+    while (an.t < an.t_min) {
+      tor_anim::anim_step_clock(an);
+      ++nsteps;
+    }
+    an.started = true;
+  } else {
+    for (int i = 0; i < A->skip; ++i) tor_anim::anim_step_clock(an);
+    nsteps = A->skip;
+  }
+  if (!(an.t < an.t_max)) return 0;
+  TOR_CUDA(ctx, cudaSetDevice(A->dev));
+  if (!A->timing_open) {
+    TOR_CUDA(ctx, cudaEventRecord(A->ev_t0, A->phys));
+    A->timing_open = true;
+  }
+  if (nsteps > 0 && A->n_dyn > 0) {
+    tor::anim_step_kernel<<<(unsigned)((A->n_dyn + 255) / 256), 256, 0, A->phys>>>(
+        A->d_vel, A->d_pos, A->d_rest, A->n_dyn, nsteps, (double)an.dt, 9.80665 * (double)an.dt);
+    TOR_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+  }
+  if (frame_index) *frame_index = A->frame;
+  const int64_t f = A->frame++;
+  if (!rgb8_out) return 1;  // this frame belongs to somebody else (frame-parallel ranks): physics only
+  const size_t k = (size_t)(A->rendered++ % (int64_t)A->slots.size());
+  tor_ctx* c = A->slots[k];
+  DeviceState& d = c->devs[0];
+  int rc = check_canvas_dims(ctx, an.nrows, an.ncols, samples_per_pixel, max_depth, 0, an.nrows, 1);
+  if (rc) return rc;
+  // the slot's previous frame must be out of its blob before the refit rewrites it
+  if (d.busy) TOR_CUDA(ctx, cudaStreamWaitEvent(A->phys, d.ev_busy, 0));
+  tor::AnimRefitParams R;
+  R.blob = d.d_blob;
+  R.bv = c->bvh.view;
+  R.pos_y = A->d_pos;
+  R.radius = A->d_rad;
+  R.rec_dyn = A->d_rec_dyn;
+  R.node_order = A->d_node_order;
+  R.level_off = A->d_level_off;
+  R.n_levels = A->n_levels;
+  R.pad = A->pad;
+  R.s_limit = A->s_limit;
+  R.node_y = A->d_node_y;
+  R.flag = A->d_flag;
+  tor::anim_refit_kernel<<<1, 1024, 0, A->phys>>>(R);
+  TOR_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  TOR_CUDA(ctx, cudaEventRecord(A->ev_ready[k], A->phys));
+  TOR_CUDA(ctx, cudaStreamWaitEvent(d.stream, A->ev_ready[k], 0));
+  tor_anim::animation_camera(an, &c->cam);  // a kernel parameter: no copy
+  (void)f;
+  rc = enqueue_rgb8(c, an.nrows, an.ncols, samples_per_pixel, gamma_correction, max_depth, flags, rgb8_out);
+  if (rc) return fail(ctx, rc, c->err);
+  return 1;
+}
+
+int tor_animation_dev_sync(tor_animation_dev* A, float* elapsed_ms) {
+  if (!A) return TOR_ERR_INVALID_ARG;
+  tor_ctx* ctx = A->parent;
+  TOR_CUDA(ctx, cudaSetDevice(A->dev));
+  for (tor_ctx* c : A->slots)
+    if (c->devs[0].busy) TOR_CUDA(ctx, cudaStreamWaitEvent(A->phys, c->devs[0].ev_busy, 0));
+  if (A->timing_open) TOR_CUDA(ctx, cudaEventRecord(A->ev_t1, A->phys));
+  TOR_CUDA(ctx, cudaStreamSynchronize(A->phys));
+  for (tor_ctx* c : A->slots) {
+    int rc = tor_sync(c);
+    if (rc) return fail(ctx, rc, c->err);
+  }
+  if (elapsed_ms) {
+    *elapsed_ms = 0.f;
+    if (A->timing_open) TOR_CUDA(ctx, cudaEventElapsedTime(elapsed_ms, A->ev_t0, A->ev_t1));
+  }
+  A->timing_open = false;
+  int32_t flag = 0;
+  TOR_CUDA(ctx, cudaMemcpy(&flag, A->d_flag, sizeof(flag), cudaMemcpyDeviceToHost));
+  if (flag) return fail(ctx, TOR_ERR_INVALID_ARG, "animation: a sphere left the range the box padding was derived for");
+  return TOR_OK;
+}
+
+int64_t tor_animation_dev_launch_count(const tor_animation_dev* A) {
+  if (!A) return 0;
+  int64_t n = 0;
+  for (tor_ctx* c : A->slots) n += c->launches;
+  return n;
 }
 
 }  // extern "C"

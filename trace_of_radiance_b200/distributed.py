@@ -39,6 +39,34 @@ def gather_rows(local, nrows, group=None, out=None):
     return uninterleave(gathered, nrows)
 
 
+def gather_rows_to(local, nrows, dst=0, group=None, out=None):
+    """The same exchange with ONE receiver: rank `dst` gets the slots tensor (G, rows_per_rank, ncols, 3) — slot g holds
+    rows g, g + G, ... compactly — and every other rank gets None.  Nothing is replicated and nothing is
+    un-interleaved on the device: scatter_slots_to_canvas / DistributedRenderer.render land the slots in the caller's
+    canvas with one strided copy each.  One collective (NCCL: grouped send / recv)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    rpr = rows_per_rank(nrows, world)
+    assert local.shape[0] == rpr
+    if rank == dst:
+        slots = out if out is not None else torch.empty((world,) + tuple(local.shape), dtype=local.dtype,
+                                                        device=local.device)
+        dist.gather(local.contiguous(), gather_list=list(slots.unbind(0)), dst=dst, group=group)
+        return slots
+    dist.gather(local.contiguous(), gather_list=None, dst=dst, group=group)
+    return None
+
+
+def scatter_slots_to_canvas(slots, pixels):
+    """Host-side un-interleave for CPU tensors / arrays: slot g's rows go to canvas rows g, g + G, ..."""
+    world = slots.shape[0]
+    nrows = pixels.shape[0]
+    for g in range(world):
+        n = (nrows - g + world - 1) // world if nrows > g else 0
+        pixels[g::world] = slots[g][:n]
+    return pixels
+
+
 def uninterleave(gathered, nrows):
     """(G, rpr, ncols, 3) -> (nrows, ncols, 3): row r lives at [r mod G, r div G]."""
     world, rpr = gathered.shape[0], gathered.shape[1]
@@ -47,7 +75,7 @@ def uninterleave(gathered, nrows):
 
 
 class DistributedRenderer:
-    """`render()` for a torchrun job: every rank calls it with the same arguments; each returns the full image."""
+    """`render()` for a torchrun job: every rank calls it with the same arguments; rank 0 ends up with the image."""
 
     def __init__(self, ctx, device=None, group=None):
         self.ctx = ctx
@@ -56,37 +84,52 @@ class DistributedRenderer:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._local = None
-        self._gathered = None
+        self._slots = None
 
     def _buffers(self, nrows, ncols):
         rpr = rows_per_rank(nrows, self.world)
         shape = (rpr, ncols, 3)
         if self._local is None or tuple(self._local.shape) != shape:
             self._local = torch.zeros(shape, dtype=torch.float64, device=self.device)
-            self._gathered = torch.empty((self.world,) + shape, dtype=torch.float64, device=self.device)
-        return self._local, self._gathered
+            self._slots = (torch.empty((self.world,) + shape, dtype=torch.float64, device=self.device)
+                           if self.rank == 0 and self.world > 1 else None)
+        return self._local, self._slots
 
     def upload(self, cam, world_list):
         self.ctx.scene_upload(cam, world_list)
 
     def render_device(self, nrows, ncols, spp, gamma, max_depth, flags=0):
-        """Scene already uploaded.  Enqueues kernel (+ gather) on torch's current stream; returns the device image."""
-        local, gathered = self._buffers(nrows, ncols)
+        """Scene already uploaded.  Enqueues kernel (+ the gather to rank 0) on torch's current stream.  Returns the
+        slots tensor (G, rows_per_rank, ncols, 3) on rank 0 — for G == 1 that is the image itself with a leading
+        axis of 1 — and None on the other ranks."""
+        local, slots = self._buffers(nrows, ncols)
         rows, _ = partition_rows(nrows, self.rank, self.world)
         stream = torch.cuda.current_stream(self.device)
         self.ctx.render_device_async(local.data_ptr(), nrows, ncols, spp, gamma, max_depth, flags, rows=rows,
                                      stream=stream.cuda_stream)
         if self.world == 1:
-            return local[:nrows]
-        return gather_rows(local, nrows, group=self.group, out=gathered)
+            return local[:nrows].unsqueeze(0)
+        return gather_rows_to(local, nrows, dst=0, group=self.group, out=slots)
+
+    def image(self, slots, nrows):
+        """The (nrows, ncols, 3) device image from render_device's slots (a copy when G > 1; for checks, not for the
+        timed path)."""
+        return uninterleave(slots, nrows).contiguous()
 
     def render(self, canvas, cam, world_list, max_depth, flags=0):
-        """Host-to-host: upload the scene, render this rank's rows, gather, copy the image into canvas.pixels."""
+        """Host-to-host: upload the scene, render this rank's rows, gather to rank 0, and on rank 0 copy slot g
+        straight into canvas rows g, g + G, ... (one strided device-to-host copy per slot).  canvas.pixels is only
+        written on rank 0."""
         self.upload(cam, world_list)
-        img = self.render_device(canvas.nrows, canvas.ncols, canvas.samples_per_pixel, canvas.gamma_correction,
-                                 max_depth, flags)
-        host = torch.from_numpy(canvas.pixels)
-        host.copy_(img, non_blocking=False)
+        nrows, ncols = canvas.nrows, canvas.ncols
+        slots = self.render_device(nrows, ncols, canvas.samples_per_pixel, canvas.gamma_correction, max_depth, flags)
+        stream = torch.cuda.current_stream(self.device)
+        if slots is not None:
+            for g in range(self.world):
+                n = (nrows - g + self.world - 1) // self.world if nrows > g else 0
+                self.ctx.download_rows_async(slots[g].data_ptr(), canvas.pixels, ncols, g, self.world, n,
+                                             stream=stream.cuda_stream)
+        stream.synchronize()
         return canvas
 
 
