@@ -530,7 +530,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-split-stream", action="store_true", help="skip the split_stream_mode leg")
-    ap.add_argument("--in-flight", type=int, default=4, help="c4: animation frames enqueued at once per GPU")
+    ap.add_argument("--in-flight", type=int, default=8, help="c4: animation frames enqueued at once per GPU")
     ap.add_argument("--ref-full-seconds", type=float, default=240.0,
                     help="--impl reference renders the whole frame in its first step when the probe predicts at most "
                          "this many seconds")

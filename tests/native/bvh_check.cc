@@ -264,7 +264,9 @@ int64_t bvh_check_rays_coop(const tor_hittable* objs, int n, const tor_camera* c
   const float* oboxes = (const float*)(pb.blob.data() + bv.off_oboxes);
   if (bv.n_clusters != (bv.n_tree_objs + 31) / 32 || bv.ncl_pad % 32 || bv.ncl_pad < bv.n_clusters) return -2;
   if (bv.off_oboxes != bv.off_cboxes + 24u * (uint32_t)bv.ncl_pad) return -3;
-  if (bv.hot_bytes != bv.off_oboxes + 768u * (uint32_t)bv.n_clusters || bv.off_objs != bv.hot_bytes) return -4;
+  if (bv.boxes_bytes != 24u * (uint32_t)bv.ncl_pad + 768u * (uint32_t)bv.n_clusters) return -4;
+  if (bv.off_cboxes != bv.lane_bytes || bv.total_bytes != bv.lane_bytes + bv.boxes_bytes || bv.off_objs != bv.nodes_bytes)
+    return -4;
   int64_t bad = 0;
   for (int64_t ri = 0; ri < nrays; ++ri) {
     const double* o = rays + 7 * ri;
@@ -342,7 +344,7 @@ uint64_t bvh_blob_hash(const tor_hittable* objs, int n, const tor_camera* cam, i
     }
   };
   feed(pb.view.off_nodes, pb.view.off_nodes + (size_t)pb.view.n_nodes * sizeof(BvhNode));
-  feed(pb.view.off_objs, pb.view.total_bytes);
+  feed(pb.view.off_objs, pb.view.lane_bytes);
   return h;
 }
 

@@ -683,9 +683,13 @@ class DeviceAnimation:
         f = 0
         while max_frames is None or f < max_frames:
             mine = f % world == rank
+            spare = False
             if mine:
                 if out is not None:
-                    buf = out[n_mine]
+                    try:
+                        buf = out[n_mine]
+                    except IndexError:  # `out` is full: this call can only be the one that finds the iterator exhausted
+                        buf, spare = self.bufs[0].array, True
                 else:
                     k = n_mine % self.in_flight
                     if len(pending) == self.in_flight:  # the buffer is still owned by a frame in flight
@@ -700,6 +704,8 @@ class DeviceAnimation:
                 idx = self.next(samples_per_pixel, max_depth, gamma_correction, flags, render=False)
             if idx is None:
                 break
+            if spare:
+                raise ValueError("render_all: `out` holds fewer frames than this rank renders")
             if mine:
                 if out is None:
                     pending.append((idx, n_mine % self.in_flight))

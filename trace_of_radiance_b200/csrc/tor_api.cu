@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -46,6 +47,9 @@ struct Tuning {
   int coop_mode = 1;           // TOR_BVH_COOP_MODE: 0 = cooperative warps spread over all CTAs, 1 = whole SMs set aside
   int coop_wc = 4;             // TOR_BVH_COOP_WC: cooperative warps per CTA of a set-aside SM (1, 2, 4 or 8)
   int coop_px_per_lane = 4;    // TOR_BVH_COOP_PXLANE: cooperative pixels only when the launch has fewer pixels per lane
+  int anim_grid_divisor = 0;   // TOR_ANIM_GRID_DIV: share of the GPU a frame in flight takes, as a divisor (0 = in_flight / 2)
+  int stage_max = 2;           // TOR_BVH_STAGE: most the kernels stage in shared memory (2 = nodes + records, 1 = nodes,
+                               //   0 = nothing; what is not staged is served by L1 / L2)
 
   static Tuning from_env() {
     Tuning t;
@@ -80,6 +84,8 @@ struct Tuning {
     t.prepass_min_spp = clampi(geti("TOR_BVH_PREPASS_SPP", 256), 9, 1 << 30);
     t.coop_mode = geti("TOR_BVH_COOP_MODE", 1) ? 1 : 0;
     t.coop_px_per_lane = clampi(geti("TOR_BVH_COOP_PXLANE", 4), 0, 1 << 20);
+    t.stage_max = clampi(geti("TOR_BVH_STAGE", 2), 0, 2);
+    t.anim_grid_divisor = clampi(geti("TOR_ANIM_GRID_DIV", 0), 0, 64);
     {
       int w = geti("TOR_BVH_COOP_WC", 4);
       t.coop_wc = (w == 1 || w == 2 || w == 4 || w == 8) ? w : 4;
@@ -137,6 +143,10 @@ struct tor_ctx {
   uint64_t trav_counters[2] = {0, 0};
   bool counters_pending = false;
   Tuning tune;
+  // > 1: this context is one of several that render concurrently on the same GPU (frames of an animation in flight):
+  // its launches take only 1/grid_divisor of the persistent grid, so that the frames' kernels are resident together
+  // and the lanes a frame's cheap pixels free up early are not held idle until its slowest pixel is done.
+  int grid_divisor = 1;
 };
 
 namespace {
@@ -186,22 +196,26 @@ LaunchPlan plan_for(const tor::SceneView& sv, int max_smem_optin) {
 // The hierarchy is staged in shared memory only while two CTAs still fit on an SM (the traversal is
 // latency-bound and wants the warps); beyond that the nodes and box tables, then nothing, and L1/L2 serve the rest.
 template <int B, bool CHUNKED, bool COOP>
-BvhLaunchPlan bvh_plan_b(const tor::BvhView& bv, size_t budget) {
-  if (bv.total_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<B, 2, CHUNKED, COOP>, 2, bv.total_bytes, B};
-  if (bv.hot_bytes <= budget) return BvhLaunchPlan{tor::render_bvh_kernel<B, 1, CHUNKED, COOP>, 1, bv.hot_bytes, B};
+BvhLaunchPlan bvh_plan_b(const tor::BvhView& bv, size_t budget, int stage_max) {
+  const tor::StagePlan s2 = tor::stage_plan<2, COOP>(bv), s1 = tor::stage_plan<1, COOP>(bv);
+  if (stage_max >= 2 && (size_t)s2.bytes0 + s2.bytes1 <= budget)
+    return BvhLaunchPlan{tor::render_bvh_kernel<B, 2, CHUNKED, COOP>, 2, (size_t)s2.bytes0 + s2.bytes1, B};
+  if (stage_max >= 1 && (size_t)s1.bytes0 + s1.bytes1 <= budget)
+    return BvhLaunchPlan{tor::render_bvh_kernel<B, 1, CHUNKED, COOP>, 1, (size_t)s1.bytes0 + s1.bytes1, B};
   return BvhLaunchPlan{tor::render_bvh_kernel<B, 0, CHUNKED, COOP>, 0, 0, B};
 }
 
 // chunked: the warp-level queue (tor_kernels_bvh.cuh); otherwise one atomic per lane.  coop: the variant with the
 // warp-cooperative pixels (exact mode with a cost-ranked order only; always chunked).
 BvhLaunchPlan bvh_plan_for(const tor::BvhView& bv, int max_smem_per_sm, int max_smem_optin, bool chunked, bool coop,
-                           int block) {
+                           int block, int stage_max) {
   // per CTA: the dynamic part + ~1.4 KB of static shared memory + 1 KB the system reserves
   const size_t half = (size_t)max_smem_per_sm / 2 - 4096;
   const size_t whole = (size_t)max_smem_optin - 2048;
-  if (block == 512) return chunked ? bvh_plan_b<512, true, false>(bv, whole) : bvh_plan_b<512, false, false>(bv, whole);
-  if (coop) return bvh_plan_b<kBlock, true, true>(bv, half);
-  return chunked ? bvh_plan_b<kBlock, true, false>(bv, half) : bvh_plan_b<kBlock, false, false>(bv, half);
+  if (block == 512)
+    return chunked ? bvh_plan_b<512, true, false>(bv, whole, stage_max) : bvh_plan_b<512, false, false>(bv, whole, stage_max);
+  if (coop) return bvh_plan_b<kBlock, true, true>(bv, half, stage_max);
+  return chunked ? bvh_plan_b<kBlock, true, false>(bv, half, stage_max) : bvh_plan_b<kBlock, false, false>(bv, half, stage_max);
 }
 
 // A multiplier m coprime to n with m/n near the golden ratio: i -> i*m mod n is a bijection of [0, n) that sends
@@ -436,7 +450,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     P.chunk = (uint32_t)tune.chunk;
 
     BvhLaunchPlan plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin, /*chunked=*/sub_log2 != 0,
-                                      /*coop=*/false, tune.block);
+                                      /*coop=*/false, tune.block, tune.stage_max);
     const int block = plan.block;
     BvhLaunchPlan main_plan = plan;  // the cost pre-pass always runs `plan`; the main launch may use another variant
     TOR_CUDA(ctx, cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
@@ -444,6 +458,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     TOR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, plan.fn, block, plan.smem));
     if (per_sm < 1) return fail(ctx, TOR_ERR_CUDA, "render kernel does not fit on an SM");
     unsigned long long cap = (unsigned long long)d.sm_count * (unsigned long long)per_sm;
+    if (ctx->grid_divisor > 1) cap = std::max<unsigned long long>(1ull, cap / (unsigned long long)ctx->grid_divisor);
     const unsigned long long want_b = ((total_px << sub_log2) + block - 1) / block;
     int grid = (int)(want_b < cap ? want_b : cap);
     if (timed) TOR_CUDA(ctx, cudaEventRecord(d.ev0, stream));
@@ -551,7 +566,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
         tor::cost_scatter_ordered_kernel<<<8, 1024, 0, stream>>>(d_rank_cost, n, d.d_hist, d.d_order, warps, group, 1u,
                                                               d.d_sched, d.d_coop, lay);
         main_plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin, /*chunked=*/true, /*coop=*/coop_max > 0,
-                                 tune.block);
+                                 tune.block, tune.stage_max);
         TOR_CUDA(ctx, cudaFuncSetAttribute(main_plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)main_plan.smem));
         P.chunk = 32;
@@ -1151,6 +1166,7 @@ int tor_animation_dev_create(tor_ctx* ctx, uint64_t seed, int32_t height, int32_
     int rc = tor_ctx_create(&A->dev, 1, &c);
     if (rc) return bail(rc, tor_last_error(nullptr));
     A->slots.push_back(c);
+    c->grid_divisor = A->parent->tune.anim_grid_divisor > 0 ? A->parent->tune.anim_grid_divisor : std::max(1, in_flight / 2);
     c->objs = objs;
     c->bvh = bvh;
     c->cam = cam;

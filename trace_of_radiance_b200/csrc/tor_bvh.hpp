@@ -15,8 +15,10 @@
 //   * objects whose box is not finite (NaN / inf centres, zero-length time interval) are not put in the
 //     tree at all: they sit in an "always" list that every segment tests exactly.
 //
-// Blob layout:  [BvhNode x n_nodes][cluster boxes][object boxes][ObjRec x n_objects (tree leaves first, then the
-//               "always" list)]
+// Blob layout:  [BvhNode x n_nodes][ObjRec x n_objects (tree leaves first, then the "always" list)][cluster boxes]
+//               [object boxes]
+// (the box tables come last: kernels without cooperative warps stage only the prefix in shared memory, which leaves
+// more of the SM's L1 to the traversal stacks in local memory)
 //
 // The two box tables serve the warp-cooperative search of the render kernel (one warp traces one expensive
 // pixel, tor_kernels_bvh.cuh): tree records are in leaf order, i.e. spatially sorted, so 32 consecutive records
@@ -83,7 +85,9 @@ struct BvhView {  // kernel parameter
   int32_t n_objects;      // records [n_tree_objs, n_objects) are the "always" list
   int32_t has_movers;
   uint32_t off_nodes, off_objs;
-  uint32_t hot_bytes;     // blob prefix holding the nodes and the two box tables
+  uint32_t nodes_bytes;   // blob prefix holding the nodes
+  uint32_t lane_bytes;    // blob prefix holding nodes + records: all that kernels without cooperative warps read
+  uint32_t boxes_bytes;   // the two box tables (cluster boxes, then object boxes), contiguous at the end of the blob
   uint32_t total_bytes;
   uint32_t off_cboxes, off_oboxes;  // cluster boxes float[6][ncl_pad]; object boxes float[n_clusters][6][32]
   int32_t n_clusters, ncl_pad;      // clusters of 32 consecutive tree records; ncl_pad = n_clusters rounded up to 32
@@ -566,13 +570,15 @@ static inline bool pack_bvh(const std::vector<tor_hittable>& objs, const tor_cam
   v.n_objects = n;
   v.has_movers = has_movers ? 1 : 0;
   v.off_nodes = 0;
-  v.off_cboxes = (uint32_t)(nodes.size() * sizeof(BvhNode));
+  v.nodes_bytes = (uint32_t)(nodes.size() * sizeof(BvhNode));
+  v.off_objs = v.nodes_bytes;
+  v.lane_bytes = v.off_objs + (uint32_t)(recs.size() * sizeof(ObjRec));
+  v.off_cboxes = v.lane_bytes;
   v.off_oboxes = v.off_cboxes + (uint32_t)(cboxes.size() * sizeof(float));
-  v.hot_bytes = v.off_oboxes + (uint32_t)(oboxes.size() * sizeof(float));
+  v.boxes_bytes = (uint32_t)((cboxes.size() + oboxes.size()) * sizeof(float));
+  v.total_bytes = v.off_cboxes + v.boxes_bytes;
   v.n_clusters = n_clusters;
   v.ncl_pad = ncl_pad;
-  v.off_objs = v.hot_bytes;
-  v.total_bytes = v.off_objs + (uint32_t)(recs.size() * sizeof(ObjRec));
   v.s_limit = bvh_detail::f32_down(1.001 * S);  // the padding was sized for origins within S (see header)
   v.max_depth = B.max_depth;
   out->blob.resize(v.total_bytes);  // nodes + box tables + records cover every byte

@@ -208,6 +208,18 @@ __device__ __forceinline__ V3 rec_center(const double2* __restrict__ r, uint32_t
   return c0;
 }
 
+// What a kernel variant keeps in shared memory: [blob prefix of bytes0][box tables, bytes1].
+struct StagePlan {
+  uint32_t bytes0, bytes1;
+};
+template <int STAGE, bool COOP>
+__host__ __device__ __forceinline__ StagePlan stage_plan(const BvhView& bv) {
+  StagePlan s;
+  s.bytes0 = STAGE == 2 ? bv.lane_bytes : (STAGE == 1 ? bv.nodes_bytes : 0u);
+  s.bytes1 = (COOP && STAGE >= 1) ? bv.boxes_bytes : 0u;
+  return s;
+}
+
 // Closest hit of the current bounce segment + the per-segment constants of the sphere test.
 struct Closest {
   double a;       // d.d  (spheres.nim:30)
@@ -336,9 +348,11 @@ __device__ __forceinline__ void coop_pixels(const BvhRenderParams& P, uint32_t c
   extern __shared__ __align__(128) uint8_t smem[];
   const BvhView& bv = P.bv;
   const double2* __restrict__ recs = reinterpret_cast<const double2*>((STAGE == 2 ? smem : P.blob) + bv.off_objs);
-  const float* __restrict__ cboxes = reinterpret_cast<const float*>((STAGE >= 1 ? smem : P.blob) + bv.off_cboxes);
-  const float* __restrict__ oboxes = reinterpret_cast<const float*>((STAGE >= 1 ? smem : P.blob) + bv.off_oboxes);
-  const uint32_t cboxes_sa = smem_u32(smem) + bv.off_cboxes, oboxes_sa = smem_u32(smem) + bv.off_oboxes;
+  // the box tables sit behind the staged blob prefix (stage_plan)
+  const uint32_t box_base = STAGE >= 1 ? stage_plan<STAGE, true>(bv).bytes0 : bv.off_cboxes;
+  const float* __restrict__ cboxes = reinterpret_cast<const float*>((STAGE >= 1 ? smem : P.blob) + box_base);
+  const float* __restrict__ oboxes = cboxes + 6 * bv.ncl_pad;
+  const uint32_t cboxes_sa = smem_u32(smem) + box_base, oboxes_sa = cboxes_sa + 24u * (uint32_t)bv.ncl_pad;
   Lane L;
   L.pix = v3(0, 0, 0);
   L.att = v3(1, 1, 1);
@@ -509,20 +523,25 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
 
   const int tid = threadIdx.x;
   const BvhView& bv = P.bv;
-  const uint32_t staged_bytes = STAGE == 2 ? bv.total_bytes : (STAGE == 1 ? bv.hot_bytes : 0u);
-
+  // Staged in shared memory: STAGE 2 = nodes + records, STAGE 1 = nodes, and in both cases the box tables of the
+  // cooperative search behind them when the kernel has cooperative warps (stage_plan; coop_pixels uses the same).
+  const StagePlan stg = stage_plan<STAGE, COOP>(bv);
   if (tid == 0) {
     mbar_init(&stage_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (staged_bytes) {
+  if (stg.bytes0 + stg.bytes1) {
     if (tid == 0) {
-      mbar_expect_tx(&stage_bar, staged_bytes);
+      mbar_expect_tx(&stage_bar, stg.bytes0 + stg.bytes1);
       const uint32_t kChunk = 32768;
-      for (uint32_t off = 0; off < staged_bytes; off += kChunk) {
-        uint32_t n = staged_bytes - off < kChunk ? staged_bytes - off : kChunk;
+      for (uint32_t off = 0; off < stg.bytes0; off += kChunk) {
+        uint32_t n = stg.bytes0 - off < kChunk ? stg.bytes0 - off : kChunk;
         tma_bulk_g2s(smem + off, P.blob + off, n, &stage_bar);
+      }
+      for (uint32_t off = 0; off < stg.bytes1; off += kChunk) {
+        uint32_t n = stg.bytes1 - off < kChunk ? stg.bytes1 - off : kChunk;
+        tma_bulk_g2s(smem + stg.bytes0 + off, P.blob + bv.off_cboxes + off, n, &stage_bar);
       }
     }
     mbar_wait(&stage_bar, 0);
