@@ -134,8 +134,26 @@ int main(void) {
   if (tor_fast_substream_count(TOR_MODE_FAST, 675, 1200, 500) != 16) return 12;
   int rc = tor_ctx_create(NULL, 0, &ctx);
   printf("%d %d %s\n", tor_abi_version(), rc, rc ? tor_last_error(NULL) : "ok");
-  if (rc == TOR_OK) tor_ctx_destroy(ctx);
-  return (rc == TOR_OK || rc == TOR_ERR_NO_DEVICE) ? 0 : 13;
+  if (rc == TOR_OK) {
+    /* with a device: the drop-in call itself, the way the Nim shim makes it (render.nim:49) */
+    static tor_hittable world[485];
+    static double pixels[8 * 8 * 3];
+    tor_canvas canvas;
+    long long n = tor_random_scene(0xFACADE, 11, world, 485);
+    int i, bad = 0;
+    canvas.pixels = pixels;
+    canvas.nrows = 8;
+    canvas.ncols = 8;
+    canvas.samples_per_pixel = 4;
+    canvas.gamma_correction = 2.2f;
+    rc = tor_render(ctx, &canvas, &cam, world, n, TOR_STRIDE_FLAT, 50, TOR_MODE_EXACT);
+    for (i = 0; i < 8 * 8 * 3; ++i) bad += !(pixels[i] >= 0.0 && pixels[i] <= 1.0);
+    printf("render %d bad %d top-left %.17g\n", rc, bad, pixels[(7 * 8 + 0) * 3]);
+    tor_ctx_destroy(ctx);
+    if (rc != TOR_OK || bad) return 14;
+    return 0;
+  }
+  return rc == TOR_ERR_NO_DEVICE ? 0 : 13;
 }
 ''')
     exe = tmp_path / "consumer"

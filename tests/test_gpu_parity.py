@@ -448,3 +448,23 @@ def test_device_animation_split_stream_equals_host_pipeline(tor, gpu_ctx):
     assert sorted(a) == sorted(b) == list(range(6))
     for i in range(6):
         assert np.array_equal(a[i], b[i]), i
+
+
+def test_c_program_calls_tor_render(tor, oracle, tmp_path):
+    """A C99 program (what Nim's importc emits for the shim of INTEGRATION.md) renders an 8x8 canvas through
+    tor_render; its top-left value equals the oracle's."""
+    import shutil
+    import subprocess
+
+    import test_abi
+
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if not cc:
+        pytest.skip("no C compiler")
+    test_abi.test_header_is_plain_c_and_links_from_c(tor, tmp_path)  # builds tmp_path/consumer and checks rc == 0
+    out = subprocess.run([str(tmp_path / "consumer")], capture_output=True, text=True)
+    line = [l for l in out.stdout.splitlines() if l.startswith("render")][0].split()
+    assert line[1] == "0" and line[3] == "0"
+    world, cam = tor.random_scene().list(), _book_cam(tor)
+    ref = oracle.render(8, 8, 4, cam.as_array(), world.objects, math="det")
+    assert float(line[5]) == ref[7, 0, 0]

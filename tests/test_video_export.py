@@ -115,9 +115,27 @@ def test_h264_writer_equals_oracle_and_reference_constants(tor, oracle, tmp_path
     assert all(p.min() > 0 for fr in planes for p in fr)
 
 
-def test_h264_rejects_partial_macroblocks(tor, tmp_path):
-    with pytest.raises(tor.api.TorError):
-        tor.H264Encoder.init(100, 48, str(tmp_path / "x.264"))
+def test_h264_rejects_odd_sizes(tor, tmp_path):
+    with pytest.raises(tor.api.TorError):  # 4:2:0 needs even sizes (color_conversions.nim:201-202)
+        tor.H264Encoder.init(101, 48, str(tmp_path / "x.264"))
+
+
+def test_h264_sizes_that_are_not_multiples_of_16_are_cropped(tor, oracle, tmp_path):
+    """The reference's own "full render" preset is 576x324 (trace_of_radiance_animation.nim:122-123; 324 = 20 * 16 + 4)
+    and io/h264.nim:168 leaves cropping as a TODO.  Here the picture is coded in whole macroblocks and cropped in the
+    SPS: FFmpeg reports the true size and decodes exactly the luma that went in."""
+    cv2 = pytest.importorskip("cv2")
+    for (h, w) in [(36, 72), (324 // 9 * 2 + 2, 64), (50, 90)]:
+        path = str(tmp_path / f"crop_{w}x{h}.264")
+        frames = _test_frames(h, w, 3)
+        planes = _write_264(tor, oracle, path, frames)
+        cap = cv2.VideoCapture(path)
+        assert cap.isOpened()
+        assert (int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))) == (w, h)
+        cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+        for k in range(3):
+            ok, fr = cap.read()
+            assert ok and np.array_equal(fr.reshape(-1)[:h * w].reshape(h, w), planes[k][0]), (h, w, k)
 
 
 def test_h264_decodes_losslessly_with_ffmpeg(tor, oracle, tmp_path):

@@ -518,7 +518,7 @@ class H264Encoder:
         h = C.c_void_p()
         rc = self.L.tor_h264_open(os.fsencode(path), width, height, C.byref(h))
         if rc:
-            raise TorError(rc, f"tor_h264_open({path}, {width}x{height}): dimensions must be multiples of 16")
+            raise TorError(rc, f"tor_h264_open({path}, {width}x{height}): width and height must be even")
         self.h, self.width, self.height = h, width, height
         p, n = C.c_void_p(), C.c_int64()
         self.L.tor_h264_frame_buffer(self.h, C.byref(p), C.byref(n))

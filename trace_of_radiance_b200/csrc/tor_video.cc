@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/tor_b200.h"
@@ -79,7 +80,19 @@ std::vector<uint8_t> make_sps(int width, int height) {
   w.ue((uint32_t)((height + 15) / 16 - 1));  // pic_height_in_map_units_minus1
   w.u(1, 1);   // frame_mbs_only_flag
   w.u(1, 0);   // direct_8x8_inference_flag
-  w.u(1, 0);   // frame_cropping_flag
+  // The reference leaves cropping as a TODO (io/h264.nim:168) and its stream for a size that is not a multiple of 16
+  // lacks the last macroblock row / column.  Here the picture is coded in whole macroblocks (the edge samples
+  // repeated) and cropped back: offsets are in units of two luma samples for 4:2:0 frames (H.264 7.4.2.1.1).
+  const int crop_r = (((width + 15) / 16) * 16 - width) / 2, crop_b = (((height + 15) / 16) * 16 - height) / 2;
+  if (crop_r || crop_b) {
+    w.u(1, 1);  // frame_cropping_flag
+    w.ue(0);    // frame_crop_left_offset
+    w.ue((uint32_t)crop_r);
+    w.ue(0);    // frame_crop_top_offset
+    w.ue((uint32_t)crop_b);
+  } else {
+    w.u(1, 0);  // frame_cropping_flag (sizes that are multiples of 16: the reference's SPS byte for byte)
+  }
   w.u(1, 0);   // vui_parameters_present_flag
   w.trailing_bits();
   return w.bytes();
@@ -221,8 +234,10 @@ extern "C" {
 int tor_h264_open(const char* path, int32_t width, int32_t height, tor_h264_encoder** out) {
   if (!out) return TOR_ERR_INVALID_ARG;
   *out = nullptr;
-  // the reference writes whole macroblocks only and never sets the cropping fields (io/h264.nim:168 "TODO cropping")
-  if (!path || width <= 0 || height <= 0 || (width % 16) || (height % 16)) return TOR_ERR_INVALID_ARG;
+  // 4:2:0 needs even sizes (color_conversions.nim:201-202); sizes that are not multiples of 16 are padded to whole
+  // macroblocks and cropped in the SPS (make_sps) — the reference's own 576x324 preset
+  // (trace_of_radiance_animation.nim:122-123) is such a size
+  if (!path || width <= 0 || height <= 0 || (width % 2) || (height % 2)) return TOR_ERR_INVALID_ARG;
   FILE* f = fopen(path, "wb");
   if (!f) return TOR_ERR_INVALID_ARG;
   tor_h264_encoder* e = new tor_h264_encoder();
@@ -270,23 +285,35 @@ int tor_h264_flush_frame(tor_h264_encoder* e) {
   const uint8_t* Cr = Cb + (size_t)cw * (h / 2);
   std::vector<uint8_t>& s = e->scratch;
   s.clear();
-  s.reserve((size_t)(w / 16) * (h / 16) * 386 + 16);
+  const int mbw = (w + 15) / 16, mbh = (h + 15) / 16, ch = h / 2;
+  s.reserve((size_t)mbw * mbh * 386 + 16);
   start_code(s);
   s.insert(s.end(), e->slice_prefix.begin(), e->slice_prefix.end());
-  for (int my = 0; my < h / 16; ++my)
-    for (int mx = 0; mx < w / 16; ++mx) {
+  for (int my = 0; my < mbh; ++my)
+    for (int mx = 0; mx < mbw; ++mx) {
       if (my || mx) s.insert(s.end(), e->mb_prefix.begin(), e->mb_prefix.end());
-      for (int r = 0; r < 16; ++r) {  // pcm_sample_luma[256], raster order inside the macroblock
-        const uint8_t* src = Y + (size_t)(my * 16 + r) * w + mx * 16;
-        s.insert(s.end(), src, src + 16);
-      }
-      for (int r = 0; r < 8; ++r) {  // pcm_sample_chroma: Cb then Cr
-        const uint8_t* src = Cb + (size_t)(my * 8 + r) * cw + mx * 8;
-        s.insert(s.end(), src, src + 8);
-      }
-      for (int r = 0; r < 8; ++r) {
-        const uint8_t* src = Cr + (size_t)(my * 8 + r) * cw + mx * 8;
-        s.insert(s.end(), src, src + 8);
+      const bool inside = (mx + 1) * 16 <= w && (my + 1) * 16 <= h;
+      if (inside) {
+        for (int r = 0; r < 16; ++r) {  // pcm_sample_luma[256], raster order inside the macroblock
+          const uint8_t* src = Y + (size_t)(my * 16 + r) * w + mx * 16;
+          s.insert(s.end(), src, src + 16);
+        }
+        for (int r = 0; r < 8; ++r) {  // pcm_sample_chroma: Cb then Cr
+          const uint8_t* src = Cb + (size_t)(my * 8 + r) * cw + mx * 8;
+          s.insert(s.end(), src, src + 8);
+        }
+        for (int r = 0; r < 8; ++r) {
+          const uint8_t* src = Cr + (size_t)(my * 8 + r) * cw + mx * 8;
+          s.insert(s.end(), src, src + 8);
+        }
+      } else {  // a macroblock that sticks out of the picture: repeat the edge samples (cropped away by the SPS)
+        for (int r = 0; r < 16; ++r)
+          for (int c = 0; c < 16; ++c)
+            s.push_back(Y[(size_t)std::min(my * 16 + r, h - 1) * w + std::min(mx * 16 + c, w - 1)]);
+        for (const uint8_t* P : {Cb, Cr})
+          for (int r = 0; r < 8; ++r)
+            for (int c = 0; c < 8; ++c)
+              s.push_back(P[(size_t)std::min(my * 8 + r, ch - 1) * cw + std::min(mx * 8 + c, cw - 1)]);
       }
     }
   s.push_back(0x80);  // rbsp_slice_trailing_bits: the data is byte aligned, so stop bit + 7 zeros
