@@ -418,6 +418,10 @@ def test_device_animation_frames_equal_the_oracle(tor, oracle, gpu_ctx):
         cam_arr, objs = ref.next_frame(skip=6)
         want = oracle.quantise_rgb8(oracle.render(27, 48, 4, cam_arr, objs, math="det"))
         assert np.array_equal(frames[i], want), i
+    again = {}
+    an.reset()  # back to the first frame: the same frames once more
+    n, _ = an.render_all(samples_per_pixel=4, on_frame=lambda i, rgb: again.__setitem__(i, rgb.copy()), max_frames=4)
+    assert n == 4 and all(np.array_equal(again[i], frames[i]) for i in range(4))
     an.close()
     # every 20th frame of the whole animation on "rank 1 of 20": 285 frames are physics-only steps in between
     an = tor.DeviceAnimation(gpu_ctx, height=18, width=32, t_max=9.0, in_flight=2)

@@ -34,12 +34,10 @@ def main():
     if QUICK:
         settings.append(("default", {}))
     else:
-        for alpha in (2, 3, 5):
-            settings.append((f"spread_a{alpha}", {"TOR_BVH_COOP_MODE": 0, "TOR_BVH_COOP_ALPHA": alpha}))
-        for wc in (2, 4):
-            for alpha in (2, 3, 5):
-                settings.append((f"excl_wc{wc}_a{alpha}", {"TOR_BVH_COOP_MODE": 1, "TOR_BVH_COOP_WC": wc,
-                                                           "TOR_BVH_COOP_ALPHA": alpha}))
+        for eg in (0, 1, 4, 8, 16):
+            settings.append((f"a1_endgame{eg}", {"TOR_BVH_COOP_ALPHA": 1, "TOR_BVH_ENDGAME": eg}))
+        settings.append(("a1_eg4_max15", {"TOR_BVH_COOP_ALPHA": 1, "TOR_BVH_ENDGAME": 4, "TOR_BVH_COOP_MAX": 15}))
+        settings.append(("a1_eg4_nodeal", {"TOR_BVH_COOP_ALPHA": 1, "TOR_BVH_ENDGAME": 4, "TOR_BVH_EXACT_DEAL": 0}))
     out = {}
     for name, env in settings:
         ctx = ctx_with(env)

@@ -59,6 +59,7 @@ EXPORTED_SYMBOLS = [
     "tor_host_free", "tor_render_ycbcr420", "tor_render_ycbcr420_async", "tor_h264_open", "tor_h264_frame_buffer",
     "tor_h264_flush_frame", "tor_h264_finish", "tor_mp4_mux_h264_file", "tor_fast_substream_count", "tor_last_schedule", "tor_download_rows_async", "tor_animation_dev_create",
     "tor_animation_dev_next", "tor_animation_dev_sync", "tor_animation_dev_launch_count", "tor_animation_dev_destroy",
+    "tor_animation_dev_reset", "tor_debug_times",
 ]
 
 
@@ -131,6 +132,7 @@ def load_library():
     L.tor_get_traversal_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.tor_scene_info.argtypes = [vp, C.POINTER(C.c_int64)]
     L.tor_last_schedule.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.tor_debug_times.argtypes = [vp, vp, C.c_int64]
     L.tor_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.tor_launch_count.argtypes = [vp]
     L.tor_launch_count.restype = C.c_int64
@@ -149,6 +151,7 @@ def load_library():
                                            C.c_int32, C.POINTER(vp)]
     L.tor_animation_dev_next.argtypes = [vp, C.c_int32, C.c_float, C.c_int64, C.c_uint32, vp, C.POINTER(C.c_int64)]
     L.tor_animation_dev_sync.argtypes = [vp, C.POINTER(C.c_float)]
+    L.tor_animation_dev_reset.argtypes = [vp]
     L.tor_animation_dev_launch_count.argtypes = [vp]
     L.tor_animation_dev_launch_count.restype = C.c_int64
     L.tor_animation_dev_destroy.argtypes = [vp]
@@ -450,6 +453,12 @@ class Context:
         return {"cooperative_pixels": int(out[0]), "qualifying_pixels": int(out[1]), "prepass_segments": int(out[2]),
                 "devices": int(out[3])}
 
+    def debug_times(self):
+        """(coop (4096, 3): start, end, segments; lanes (8192, 2): start, end) in ns (tor_debug_times)."""
+        out = np.zeros(3 * 4096 + 2 * 8192, dtype=np.uint64)
+        self._check(self.L.tor_debug_times(self.h, out.ctypes.data, out.size))
+        return out[:3 * 4096].reshape(4096, 3), out[3 * 4096:].reshape(8192, 2)
+
     def last_kernel_ms(self):
         ms = C.c_float()
         self._check(self.L.tor_last_kernel_ms(self.h, C.byref(ms)))
@@ -667,6 +676,10 @@ class DeviceAnimation:
         ms = C.c_float()
         self.ctx._check(self.L.tor_animation_dev_sync(self.h, C.byref(ms)))
         return float(ms.value)
+
+    def reset(self):
+        """Back to the first frame."""
+        self.ctx._check(self.L.tor_animation_dev_reset(self.h))
 
     def launch_count(self):
         return int(self.L.tor_animation_dev_launch_count(self.h)) + self.ctx.launch_count()

@@ -37,16 +37,17 @@ struct Tuning {
   bool queue_percost = false;  // TOR_BVH_EXACT_QUEUE=percost: one class per cost value, one atomic per lane
   bool no_scramble = false;    // TOR_BVH_NO_SCRAMBLE: row-major queue for renders without a cost pre-pass
   bool fast_scramble = false;  // TOR_BVH_FAST_SCRAMBLE: scattered queue in split-stream mode
-  float coop_alpha = 2.0f;     // TOR_BVH_COOP_ALPHA: a pixel is traced by a whole warp when its pre-pass cost
+  float coop_alpha = 1.0f;     // TOR_BVH_COOP_ALPHA: a pixel is traced by a whole warp when its pre-pass cost
                                //   exceeds alpha x the mean cost per lane of the launch
-  int coop_max_pct = 25;       // TOR_BVH_COOP_MAX: at most this percentage of the grid's warps start cooperatively
-                               //   (0 switches the mechanism off)
+  int coop_max_pct = 15;       // TOR_BVH_COOP_MAX: at most this percentage of the SMs is set aside for cooperative
+                               //   pixels, 8 per SM (0 switches the mechanism off)
   long long coop_force = -1;   // TOR_BVH_COOP_FORCE: trace exactly this many of the most expensive pixels
                                //   cooperatively (tests), still capped by coop_max_pct
   int prepass_min_spp = 256;   // TOR_BVH_PREPASS_SPP: samples per pixel from which the cost pre-pass runs
-  int coop_mode = 1;           // TOR_BVH_COOP_MODE: 0 = cooperative warps spread over all CTAs, 1 = whole SMs set aside
-  int coop_wc = 4;             // TOR_BVH_COOP_WC: cooperative warps per CTA of a set-aside SM (1, 2, 4 or 8)
-  int coop_px_per_lane = 4;    // TOR_BVH_COOP_PXLANE: cooperative pixels only when the launch has fewer pixels per lane
+  int coop_px_per_lane = 8;    // TOR_BVH_COOP_PXLANE: cooperative pixels only when the launch has fewer pixels per lane
+  int endgame_min_chunk = 4;   // TOR_BVH_ENDGAME: smallest share of the cost-ranked queue a warp takes near the end (0: off)
+  int coop_queue_factor = 4;   // TOR_BVH_COOP_QUEUE: at most this many cooperative pixels per cooperative warp
+  bool debug_times = false;    // TOR_BVH_DEBUG_TIMES: record start / end stamps of every warp (tor_debug_times)
   int anim_grid_divisor = 0;   // TOR_ANIM_GRID_DIV: share of the GPU a frame in flight takes, as a divisor (0 = in_flight / 2)
   int stage_max = 2;           // TOR_BVH_STAGE: 2 = stage nodes + records in shared memory when they fit, else nothing
                                //   (default); 1 = nodes only; 0 = nothing (everything through L1 / L2)
@@ -78,18 +79,16 @@ struct Tuning {
     t.no_scramble = getenv("TOR_BVH_NO_SCRAMBLE") != nullptr;
     t.fast_scramble = getenv("TOR_BVH_FAST_SCRAMBLE") != nullptr;
     if (const char* e = getenv("TOR_BVH_COOP_ALPHA")) t.coop_alpha = (float)atof(e);
-    if (!(t.coop_alpha > 0.f)) t.coop_alpha = 2.0f;
-    t.coop_max_pct = clampi(geti("TOR_BVH_COOP_MAX", 25), 0, 50);
+    if (!(t.coop_alpha > 0.f)) t.coop_alpha = 1.0f;
+    t.coop_max_pct = clampi(geti("TOR_BVH_COOP_MAX", 15), 0, 50);
     if (const char* e = getenv("TOR_BVH_COOP_FORCE")) t.coop_force = atoll(e);
     t.prepass_min_spp = clampi(geti("TOR_BVH_PREPASS_SPP", 256), 9, 1 << 30);
-    t.coop_mode = geti("TOR_BVH_COOP_MODE", 1) ? 1 : 0;
-    t.coop_px_per_lane = clampi(geti("TOR_BVH_COOP_PXLANE", 4), 0, 1 << 20);
+    t.coop_px_per_lane = clampi(geti("TOR_BVH_COOP_PXLANE", 8), 0, 1 << 20);
+    t.coop_queue_factor = clampi(geti("TOR_BVH_COOP_QUEUE", 4), 1, 64);
+    t.endgame_min_chunk = clampi(geti("TOR_BVH_ENDGAME", 4), 0, 32);
     t.stage_max = clampi(geti("TOR_BVH_STAGE", 2), 0, 2);
     t.anim_grid_divisor = clampi(geti("TOR_ANIM_GRID_DIV", 0), 0, 64);
-    {
-      int w = geti("TOR_BVH_COOP_WC", 4);
-      t.coop_wc = (w == 1 || w == 2 || w == 4 || w == 8) ? w : 4;
-    }
+    t.debug_times = getenv("TOR_BVH_DEBUG_TIMES") != nullptr;
     return t;
   }
 };
@@ -102,6 +101,11 @@ struct DeviceState {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_busy = nullptr;  // end of the last launch that used this device's scratch buffers (any stream)
+  cudaStream_t stream_coop = nullptr;  // render_coop_kernel runs beside the lane kernel, at a higher priority
+  cudaEvent_t ev_ranked = nullptr, ev_coop_done = nullptr;
+  unsigned long long* d_dbg = nullptr;  // TOR_BVH_DEBUG_TIMES: %globaltimer stamps of the last exact-mode main launch
+  unsigned int* d_ticket = nullptr;  // [0] arrival counter of the lane kernel's CTAs (BvhRenderParams::deal_ticket),
+                                     // [1] cooperative CTAs resident (coop_gate_kernel)
   bool busy = false;
   uint8_t* d_blob = nullptr;  // BVH blob (tor_bvh.hpp)
   size_t blob_cap = 0;
@@ -153,6 +157,13 @@ namespace {
 
 thread_local std::string g_create_err;
 
+cudaError_t create_priority_stream(cudaStream_t* s) {
+  int lo = 0, hi = 0;  // numerically lowest value = highest priority
+  cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (e != cudaSuccess) return e;
+  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, hi);
+}
+
 int fail(tor_ctx* ctx, int code, const std::string& msg) {
   if (ctx)
     ctx->err = msg;
@@ -195,30 +206,27 @@ LaunchPlan plan_for(const tor::SceneView& sv, int max_smem_optin) {
 
 // The hierarchy is staged in shared memory only while two CTAs still fit on an SM (the traversal is
 // latency-bound and wants the warps); beyond that the nodes and box tables, then nothing, and L1/L2 serve the rest.
-template <int B, bool CHUNKED, bool COOP>
+template <int B, bool CHUNKED>
 BvhLaunchPlan bvh_plan_b(const tor::BvhView& bv, size_t budget, int stage_max) {
-  const tor::StagePlan s2 = tor::stage_plan<2, COOP>(bv), s1 = tor::stage_plan<1, COOP>(bv);
+  const tor::StagePlan s2 = tor::stage_plan<2>(bv), s1 = tor::stage_plan<1>(bv);
   if (stage_max >= 2 && (size_t)s2.bytes0 + s2.bytes1 <= budget)
-    return BvhLaunchPlan{tor::render_bvh_kernel<B, 2, CHUNKED, COOP>, 2, (size_t)s2.bytes0 + s2.bytes1, B};
+    return BvhLaunchPlan{tor::render_bvh_kernel<B, 2, CHUNKED>, 2, (size_t)s2.bytes0 + s2.bytes1, B};
   // Nodes alone in shared memory (STAGE 1) is only taken on request: the records then come through an L1 that the
   // shared-memory carve-out has shrunk to ~28 KB, next to the traversal stacks; measured on 1 938 objects: 68 ms
   // against 59 ms with nothing staged and the whole 256 KB as L1.
   if (stage_max == 1 && (size_t)s1.bytes0 + s1.bytes1 <= budget)
-    return BvhLaunchPlan{tor::render_bvh_kernel<B, 1, CHUNKED, COOP>, 1, (size_t)s1.bytes0 + s1.bytes1, B};
-  return BvhLaunchPlan{tor::render_bvh_kernel<B, 0, CHUNKED, COOP>, 0, 0, B};
+    return BvhLaunchPlan{tor::render_bvh_kernel<B, 1, CHUNKED>, 1, (size_t)s1.bytes0 + s1.bytes1, B};
+  return BvhLaunchPlan{tor::render_bvh_kernel<B, 0, CHUNKED>, 0, 0, B};
 }
 
-// chunked: the warp-level queue (tor_kernels_bvh.cuh); otherwise one atomic per lane.  coop: the variant with the
-// warp-cooperative pixels (exact mode with a cost-ranked order only; always chunked).
-BvhLaunchPlan bvh_plan_for(const tor::BvhView& bv, int max_smem_per_sm, int max_smem_optin, bool chunked, bool coop,
-                           int block, int stage_max) {
+// chunked: the warp-level queue (tor_kernels_bvh.cuh); otherwise one atomic per lane.
+BvhLaunchPlan bvh_plan_for(const tor::BvhView& bv, int max_smem_per_sm, int max_smem_optin, bool chunked, int block,
+                           int stage_max) {
   // per CTA: the dynamic part + ~1.4 KB of static shared memory + 1 KB the system reserves
   const size_t half = (size_t)max_smem_per_sm / 2 - 4096;
   const size_t whole = (size_t)max_smem_optin - 2048;
-  if (block == 512)
-    return chunked ? bvh_plan_b<512, true, false>(bv, whole, stage_max) : bvh_plan_b<512, false, false>(bv, whole, stage_max);
-  if (coop) return bvh_plan_b<kBlock, true, true>(bv, half, stage_max);
-  return chunked ? bvh_plan_b<kBlock, true, false>(bv, half, stage_max) : bvh_plan_b<kBlock, false, false>(bv, half, stage_max);
+  if (block == 512) return chunked ? bvh_plan_b<512, true>(bv, whole, stage_max) : bvh_plan_b<512, false>(bv, whole, stage_max);
+  return chunked ? bvh_plan_b<kBlock, true>(bv, half, stage_max) : bvh_plan_b<kBlock, false>(bv, half, stage_max);
 }
 
 // A multiplier m coprime to n with m/n near the golden ratio: i -> i*m mod n is a bijection of [0, n) that sends
@@ -453,7 +461,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     P.chunk = (uint32_t)tune.chunk;
 
     BvhLaunchPlan plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin, /*chunked=*/sub_log2 != 0,
-                                      /*coop=*/false, tune.block, tune.stage_max);
+                                      tune.block, tune.stage_max);
     const int block = plan.block;
     BvhLaunchPlan main_plan = plan;  // the cost pre-pass always runs `plan`; the main launch may use another variant
     TOR_CUDA(ctx, cudaFuncSetAttribute(plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
@@ -526,18 +534,17 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       tor::CoopLayout lay;
       lay.grid = (uint32_t)grid;
       lay.wpc = (uint32_t)(block / 32);
-      lay.wc = (uint32_t)tune.coop_wc;
-      // whole SMs can only be set aside when the grid is exactly two CTAs on every SM
-      lay.mode = (tune.coop_mode == 1 && per_sm == 2 && grid == 2 * d.sm_count) ? 1u : 0u;
+      lay.per_sm = (uint32_t)per_sm;
+      lay.coop_grid = 0;
       // Only launches with few pixels per lane can end on a single pixel's chain (C2: a GPU's share in a 4- or
-      // 8-GPU render); with many pixels per lane the dealt first wave hides the chains, and the kernel variant
-      // without the cooperative code runs the lanes ~4 % faster (its register allocation is tighter).
+      // 8-GPU render); with many pixels per lane the dealt first wave hides the chains and the SMs are better used
+      // by the lanes.  Cooperative CTAs take whole SMs, so the grid must be the full persistent one.
       const bool few_pixels = total_px < lanes * (unsigned long long)tune.coop_px_per_lane;
-      if (coherent && warps && block == kBlock && (few_pixels || tune.coop_force >= 0)) {
-        const unsigned long long slots = lay.mode ? (unsigned long long)grid * lay.wc : warps_all;
-        coop_max = (uint32_t)(slots * (unsigned)tune.coop_max_pct / 100ull);
-        if (coop_max > slots / 2) coop_max = (uint32_t)(slots / 2);
-        if (tune.coop_force >= 0 && tune.coop_max_pct > 0) coop_max = n;
+      const bool full_grid = grid == per_sm * d.sm_count;
+      if (coherent && warps && tune.coop_max_pct > 0 && ((few_pixels && full_grid) || tune.coop_force >= 0)) {
+        lay.coop_grid = std::max(1u, (uint32_t)((unsigned long long)d.sm_count * (unsigned)tune.coop_max_pct / 100ull));
+        coop_max = lay.coop_grid * tor::kCoopWarps * (uint32_t)tune.coop_queue_factor;  // a queue: several per warp
+        if (tune.coop_force >= 0) coop_max = n;  // tests: any number of pixels, the warps loop
       }
       if (coop_max > d.coop_cap) {
         if (d.d_coop) cudaFree(d.d_coop);
@@ -568,12 +575,12 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       if (coherent) {
         tor::cost_scatter_ordered_kernel<<<8, 1024, 0, stream>>>(d_rank_cost, n, d.d_hist, d.d_order, warps, group, 1u,
                                                               d.d_sched, d.d_coop, lay);
-        main_plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin, /*chunked=*/true, /*coop=*/coop_max > 0,
-                                 tune.block, tune.stage_max);
+        main_plan = bvh_plan_for(P.bv, d.max_smem_per_sm, d.max_smem_optin, /*chunked=*/true, tune.block, tune.stage_max);
         TOR_CUDA(ctx, cudaFuncSetAttribute(main_plan.fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)main_plan.smem));
         P.chunk = 32;
         P.chunk_guard = 0;
+        P.endgame_min_chunk = (uint32_t)tune.endgame_min_chunk;
       } else {
         tor::cost_scatter_kernel<<<sort_grid, 256, 0, stream>>>(d_rank_cost, n, d.d_hist, d.d_order, warps, group,
                                                                 d.d_sched, d.d_coop, lay);
@@ -585,6 +592,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       P.sched = d.d_sched;  // sched[0] = 0 when coop_max == 0
       P.coop_list = d.d_coop;
       P.coop = lay;
+      P.deal_ticket = d.d_ticket;
     } else if (reorder && sub_log2 == 0 && !tune.no_scramble) {
       // exact mode without cost information (few samples per pixel): scatter the image over the warps so that
       // expensive neighbours do not share one (BvhRenderParams::scramble).  Split-stream units are short, so there
@@ -593,8 +601,29 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     } else if (sub_log2 && tune.fast_scramble) {
       P.scramble = coprime_near_golden((uint32_t)total_px);
     }
+    if (tune.debug_times && !P.cost) {
+      const size_t bytes = (3 * 4096 + 2 * 8192) * sizeof(unsigned long long);
+      if (!d.d_dbg) TOR_CUDA(ctx, cudaMalloc(&d.d_dbg, bytes));
+      TOR_CUDA(ctx, cudaMemsetAsync(d.d_dbg, 0, bytes, stream));
+      P.dbg_times = d.d_dbg;
+    }
+    const bool with_coop = P.sched != nullptr && P.coop.coop_grid > 0;
+    if (P.sched) TOR_CUDA(ctx, cudaMemsetAsync(d.d_ticket, 0, 4 * sizeof(unsigned int), stream));  // ticket, arrivals, queue head
+    if (with_coop) {
+      // render_coop_kernel on its own high-priority stream, launched first so that its CTAs take their SMs before the
+      // lane kernel's grid fills the GPU; it reads the ranking the kernels above left on `stream`
+      TOR_CUDA(ctx, cudaEventRecord(d.ev_ranked, stream));
+      TOR_CUDA(ctx, cudaStreamWaitEvent(d.stream_coop, d.ev_ranked, 0));
+      tor::render_coop_kernel<<<P.coop.coop_grid, tor::kCoopBlock, 0, d.stream_coop>>>(P);
+      TOR_CUDA(ctx, cudaGetLastError());
+      TOR_CUDA(ctx, cudaEventRecord(d.ev_coop_done, d.stream_coop));
+      tor::coop_gate_kernel<<<1, 1, 0, stream>>>(d.d_sched, d.d_ticket + 1, P.coop);
+      TOR_CUDA(ctx, cudaGetLastError());
+      ctx->launches += 2;
+    }
     main_plan.fn<<<grid, block, main_plan.smem, stream>>>(P);
     TOR_CUDA(ctx, cudaGetLastError());
+    if (with_coop) TOR_CUDA(ctx, cudaStreamWaitEvent(stream, d.ev_coop_done, 0));  // draw needs every pixel's sum
     const unsigned long long nch = total_px * 3ull;
     if (sub_log2) {  // per-range partial sums -> pixel sums, fixed pairwise order
       const unsigned long long nthr = nch << sub_log2;
@@ -668,6 +697,10 @@ int tor_ctx_create(const int* devices, int ndev, tor_ctx** out) {
     bool ok = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&d.ev0) == cudaSuccess && cudaEventCreate(&d.ev1) == cudaSuccess &&
               cudaEventCreateWithFlags(&d.ev_busy, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&d.ev_ranked, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&d.ev_coop_done, cudaEventDisableTiming) == cudaSuccess &&
+              create_priority_stream(&d.stream_coop) == cudaSuccess &&
+              cudaMalloc(&d.d_ticket, 4 * sizeof(unsigned int)) == cudaSuccess &&
               cudaMalloc(&d.d_work, 2 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&d.d_sched, 4 * sizeof(uint32_t)) == cudaSuccess &&
               cudaMemset(d.d_sched, 0, 4 * sizeof(uint32_t)) == cudaSuccess &&
@@ -696,6 +729,11 @@ void tor_ctx_destroy(tor_ctx* ctx) {
     if (d.d_sched) cudaFree(d.d_sched);
     if (d.d_coop) cudaFree(d.d_coop);
     if (d.ev_busy) cudaEventDestroy(d.ev_busy);
+    if (d.ev_ranked) cudaEventDestroy(d.ev_ranked);
+    if (d.ev_coop_done) cudaEventDestroy(d.ev_coop_done);
+    if (d.stream_coop) cudaStreamDestroy(d.stream_coop);
+    if (d.d_ticket) cudaFree(d.d_ticket);
+    if (d.d_dbg) cudaFree(d.d_dbg);
     if (d.d_pixels) cudaFree(d.d_pixels);
     if (d.d_work) cudaFree(d.d_work);
     if (d.d_cost) cudaFree(d.d_cost);
@@ -996,6 +1034,17 @@ int tor_last_schedule(tor_ctx* ctx, int64_t out[4]) {
   return TOR_OK;
 }
 
+int tor_debug_times(tor_ctx* ctx, uint64_t* out, int64_t n) {
+  if (!ctx || !out) return TOR_ERR_INVALID_ARG;
+  DeviceState& d = ctx->devs[0];
+  if (!d.d_dbg) return fail(ctx, TOR_ERR_INVALID_ARG, "no stamps: create the context with TOR_BVH_DEBUG_TIMES set");
+  const int64_t have = 3 * 4096 + 2 * 8192;
+  TOR_CUDA(ctx, cudaSetDevice(d.dev));
+  TOR_CUDA(ctx, cudaDeviceSynchronize());
+  TOR_CUDA(ctx, cudaMemcpy(out, d.d_dbg, (size_t)(n < have ? n : have) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return TOR_OK;
+}
+
 int tor_last_kernel_ms(tor_ctx* ctx, float* ms) {
   if (!ctx || !ms) return TOR_ERR_INVALID_ARG;
   float mx = 0.f;
@@ -1063,6 +1112,9 @@ struct tor_animation_dev {
   int64_t frame = 0;     // frames produced or skipped so far
   int64_t rendered = 0;  // frames rendered by this object
   int dev = 0;
+  std::vector<double> vel0, pos0;  // initial physics state (tor_animation_dev_reset)
+  float t0 = 0.f;
+  double angle0 = 0.0;
 };
 
 int tor_animation_dev_create(tor_ctx* ctx, uint64_t seed, int32_t height, int32_t width, float dt, float t_min,
@@ -1143,6 +1195,10 @@ int tor_animation_dev_create(tor_ctx* ctx, uint64_t seed, int32_t height, int32_
     rest.push_back(sp.coef_restitution);
     rad.push_back(sp.radius);
   }
+  A->vel0 = vel;
+  A->pos0 = pos;
+  A->t0 = A->an->t;
+  A->angle0 = A->an->look_from_angle;
   cudaError_t e = cudaSetDevice(A->dev);
   auto up = [&](auto** dptr, const auto& v) {
     using T = typename std::remove_reference<decltype(v)>::type::value_type;
@@ -1263,6 +1319,26 @@ int tor_animation_dev_next(tor_animation_dev* A, int32_t samples_per_pixel, floa
   rc = enqueue_rgb8(c, an.nrows, an.ncols, samples_per_pixel, gamma_correction, max_depth, flags, rgb8_out);
   if (rc) return fail(ctx, rc, c->err);
   return 1;
+}
+
+int tor_animation_dev_reset(tor_animation_dev* A) {
+  if (!A) return TOR_ERR_INVALID_ARG;
+  tor_ctx* ctx = A->parent;
+  int rc = tor_animation_dev_sync(A, nullptr);
+  if (rc) return rc;
+  TOR_CUDA(ctx, cudaSetDevice(A->dev));
+  // back to the first frame: the initial velocities and heights (two small arrays, once per animation, not per frame)
+  if (A->n_dyn > 0) {
+    TOR_CUDA(ctx, cudaMemcpyAsync(A->d_vel, A->vel0.data(), A->vel0.size() * sizeof(double), cudaMemcpyHostToDevice, A->phys));
+    TOR_CUDA(ctx, cudaMemcpyAsync(A->d_pos, A->pos0.data(), A->pos0.size() * sizeof(double), cudaMemcpyHostToDevice, A->phys));
+    TOR_CUDA(ctx, cudaStreamSynchronize(A->phys));
+  }
+  A->an->t = A->t0;
+  A->an->look_from_angle = A->angle0;
+  A->an->started = false;
+  A->frame = 0;
+  A->rendered = 0;
+  return TOR_OK;
 }
 
 int tor_animation_dev_sync(tor_animation_dev* A, float* elapsed_ms) {

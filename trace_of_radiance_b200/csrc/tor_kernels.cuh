@@ -210,7 +210,10 @@ struct Surface {
 
 // Record fill (spheres.nim:41-46, core.nim:47-49) + scatter (materials.nim:24-86) + render.nim:35-38.
 // Returns true when the sample ends here (absorbed, or depth exhausted -> black).
-__device__ __forceinline__ bool shade_hit(Lane& L, double best_t, const Surface& S, int32_t max_depth) {
+// ud_pre: unit_vector(L.d) when the caller has it already (Metal, Dielectric and the sky all need it: the BVH kernel
+// computes it once per segment for all of them together), else NULL.
+__device__ __forceinline__ bool shade_hit(Lane& L, double best_t, const Surface& S, int32_t max_depth,
+                                          const V3* ud_pre = nullptr) {
   const V3 o = L.o, d = L.d;
   V3 p = o + best_t * d;
   V3 outward = (p - S.center) * S.inv_r;
@@ -230,7 +233,7 @@ __device__ __forceinline__ bool shade_hit(Lane& L, double best_t, const Surface&
     ntime = L.time;
     matt = S.albedo;
   } else if (S.mat_kind == TOR_METAL) {  // materials.nim:39-47
-    V3 refl = reflect(unit_vector(d), n);
+    V3 refl = reflect(ud_pre ? *ud_pre : unit_vector(d), n);
     V3 s;
     for (;;) {  // sampling.nim:45-49
       s.x = rng_urange(L.rng, -1, 1);
@@ -244,7 +247,7 @@ __device__ __forceinline__ bool shade_hit(Lane& L, double best_t, const Surface&
   } else {  // materials.nim:62-86
     double ior = S.fuzz_or_ior;
     double eta = front_face ? 1.0 / ior : ior;
-    V3 ud = unit_vector(d);
+    V3 ud = ud_pre ? *ud_pre : unit_vector(d);
     double dt = dot(-ud, n);
     double cos_theta = (dt <= 1.0) ? dt : 1.0;
     double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
@@ -276,8 +279,8 @@ __device__ __forceinline__ bool shade_hit(Lane& L, double best_t, const Surface&
 }
 
 // render.nim:40-45 — the ray left the scene: sky colour times the attenuation so far
-__device__ __forceinline__ V3 shade_miss(const Lane& L) {
-  V3 ud = unit_vector(L.d);
+__device__ __forceinline__ V3 shade_miss(const Lane& L, const V3* ud_pre = nullptr) {
+  V3 ud = ud_pre ? *ud_pre : unit_vector(L.d);
   double t = 0.5 * ud.y + 1.0;
   V3 color = v3((1.0 - t) + t * 0.5, (1.0 - t) + t * 0.7, (1.0 - t) + t);
   color.x *= L.att.x;

@@ -29,67 +29,28 @@
 
 namespace tor {
 
-// Which warps of the render grid start cooperatively (one expensive pixel per warp, see the kernel) and which are
-// dealt pixels lane by lane.  Shared by the render kernel and the scatter kernels that lay the ranked pixels out.
-//   mode 0 "spread": cooperative warps are the first min(K, warps) ranks, rank = warp-in-CTA * grid + CTA, i.e. one per
-//          CTA before any CTA gets a second one.
-//   mode 1 "exclusive": whole SMs are set aside.  The grid is 2 CTAs per SM and CTAs b and b + grid/2 are taken to
-//          share an SM (the block scheduler fills the SMs breadth-first; nothing breaks if it does not, the warps
-//          merely share schedulers with other work).  The first ceil(K / (2 * wc)) SMs run `wc` cooperative warps per
-//          CTA and nothing else until those are done: a cooperative warp is a serial dependency chain, and every
-//          other warp on its scheduler takes issue slots from it.
+// Cooperative pixels run in their OWN kernel (render_coop_kernel below): one CTA of 512 threads per SM that is set
+// aside — with 128 registers per thread such a CTA takes the SM's whole register file, so no CTA of the lane kernel can
+// share the SM, and only kCoopWarps of its warps (two per scheduler) do any work: a cooperative warp is a serial
+// dependency chain and every other warp on its scheduler takes issue slots from it.  The lane kernel is launched with
+// its usual grid; its CTAs that find no SM free start when the cooperative CTAs are done and go straight to the
+// queue.  CoopLayout tells both kernels and the scatter kernels how the ranked pixels are laid out.
+static constexpr uint32_t kCoopWarps = 8;    // working warps per cooperative CTA
+static constexpr uint32_t kCoopBlock = 512;  // threads per cooperative CTA (fills an SM's register file)
 struct CoopLayout {
-  uint32_t mode, grid, wpc, wc;  // wpc = warps per CTA, wc = cooperative warps per cooperative CTA (mode 1)
+  uint32_t coop_grid;  // CTAs of the cooperative kernel (0: no cooperative pixels in this launch)
+  uint32_t grid, wpc;  // lane kernel: CTAs and warps per CTA
+  uint32_t per_sm;     // lane-kernel CTAs that one cooperative CTA keeps off its SM
 };
-struct WarpRole {
-  uint32_t coop_first, coop_stride;  // cooperative pixels coop_first, coop_first + coop_stride, ... < K (0xffffffff: none)
-  uint32_t deal_rank;                // 0xffffffff: this warp is dealt nothing
-  bool coop_cta;                     // mode 1: the CTA waits on a named barrier until its cooperative warps are done
-};
-__host__ __device__ __forceinline__ uint32_t coop_sms(const CoopLayout& c, uint32_t K) {
-  const uint32_t n_sm = c.grid / 2u, per_sm = 2u * c.wc;
-  const uint32_t want = (K + per_sm - 1u) / per_sm;
-  return want < n_sm ? want : n_sm;
+// cooperative CTAs that get pixels when K pixels are cooperative
+__host__ __device__ __forceinline__ uint32_t coop_ctas_used(const CoopLayout& c, uint32_t K) {
+  const uint32_t want = (K + kCoopWarps - 1u) / kCoopWarps;
+  return want < c.coop_grid ? want : c.coop_grid;
 }
-// number of warps that are dealt pixels when K pixels are cooperative
+// warps of the lane kernel that are dealt pixels: those of the CTAs that start at once
 __host__ __device__ __forceinline__ uint32_t deal_warps(const CoopLayout& c, uint32_t K) {
-  const uint32_t warps = c.grid * c.wpc;
-  if (c.mode == 0u) return warps - (K < warps ? K : warps);
-  return (c.grid - 2u * coop_sms(c, K)) * c.wpc;
-}
-__device__ __forceinline__ WarpRole warp_role(const CoopLayout& c, uint32_t K, uint32_t b, uint32_t w) {
-  WarpRole r;
-  r.coop_first = 0xffffffffu;
-  r.coop_stride = 1u;
-  r.coop_cta = false;
-  if (c.mode == 0u) {
-    const uint32_t warps = c.grid * c.wpc, cw = K < warps ? K : warps, rank = w * c.grid + b;
-    if (rank < cw) {
-      r.coop_first = rank;
-      r.coop_stride = warps;
-      r.deal_rank = 0xffffffffu;
-    } else {
-      r.deal_rank = rank - cw;
-    }
-    return r;
-  }
-  const uint32_t n_sm = c.grid / 2u, sm = b % n_sm, half = b / n_sm, n_csm = coop_sms(c, K);
-  if (sm < n_csm) {
-    r.coop_cta = true;
-    r.deal_rank = 0xffffffffu;
-    // the two CTAs of an SM take different warp indices so that their cooperative warps sit on different schedulers
-    // when wc < 4 (warp slot mod 4 selects the scheduler)
-    const uint32_t w0 = (half * c.wc) % c.wpc;
-    const uint32_t k = (w + c.wpc - w0) % c.wpc;  // position among this CTA's cooperative warps
-    if (k < c.wc) {
-      const uint32_t n_cta = 2u * n_csm;
-      r.coop_first = k * n_cta + (sm * 2u + half);  // the most expensive pixels go to different SMs
-      r.coop_stride = n_cta * c.wc;
-    }
-  } else {
-    r.deal_rank = ((sm - n_csm) * 2u + half) * c.wpc + w;
-  }
-  return r;
+  const uint32_t late = coop_ctas_used(c, K) * c.per_sm;
+  return (late < c.grid ? c.grid - late : 0u) * c.wpc;
 }
 
 struct BvhRenderParams {
@@ -121,14 +82,18 @@ struct BvhRenderParams {
   // cooperative; with n_coop cooperative warps (below) the region is 32 * (warps - n_coop) entries and the queue
   // starts right behind it.  Both the scatter kernels and this kernel derive the layout from sched[0].
   uint32_t first_wave;
-  // Warp-cooperative pixels (exact mode, COOP kernels).  sched[0] = n_coop, computed on the device from the cost
-  // histogram (cost_offsets_kernel): the n_coop most expensive pixels are not given to single lanes; pixel
-  // coop_list[r] is traced by the whole warp with rank r (rank = warp-in-CTA * gridDim.x + blockIdx.x, which spreads
-  // them over all SMs), whose lanes share the closest-hit search of every bounce segment.  Those warps join the
-  // ordinary queue afterwards.  NULL = no cooperative pixels.
+  // Warp-cooperative pixels (exact mode).  sched[0] = n_coop, computed on the device from the cost histogram
+  // (cost_offsets_kernel): the n_coop most expensive pixels are not given to single lanes; render_coop_kernel traces
+  // pixel coop_list[k] with a whole warp whose lanes share the closest-hit search of every bounce segment.
+  // NULL = no cooperative pixels.  deal_ticket[0]: the lane kernel's CTAs take their dealing rank in arrival order;
+  // [1]: cooperative CTAs resident (coop_gate_kernel); [2]: head of the cooperative pixel queue.
   const uint32_t* sched;
   const uint32_t* coop_list;
   CoopLayout coop;
+  unsigned int* deal_ticket;
+  // Developer aid (NULL in production): %globaltimer stamps — [3k..3k+2] = start, end, segments of cooperative warp k
+  // (k = CTA * kCoopWarps + warp) and, from entry 3 * 4096 on, [2w], [2w+1] = start and end of lane-kernel warp w.
+  unsigned long long* dbg_times;
   // Lanes of each warp that take pixels (1..32; 32 unless the TOR_BVH_LANES tuning knob says otherwise).
   int32_t lanes_per_warp;
   // Split-stream mode (TOR_MODE_FAST, include/tor_b200.h): every pixel's sample loop is cut into 2^sub_log2
@@ -141,6 +106,7 @@ struct BvhRenderParams {
   // end of the queue below which warps take 32 at a time so that the render does not end on one warp's long chunk.
   uint32_t chunk;
   unsigned long long chunk_guard;
+  uint32_t endgame_min_chunk;  // cost-ranked queue: smallest share a warp takes near the end (0: always `chunk`)
 };
 
 // One object of a leaf (or of the "always" list) against the ray: the reference's arithmetic
@@ -212,11 +178,12 @@ __device__ __forceinline__ V3 rec_center(const double2* __restrict__ r, uint32_t
 struct StagePlan {
   uint32_t bytes0, bytes1;
 };
-template <int STAGE, bool COOP>
+template <int STAGE>
 __host__ __device__ __forceinline__ StagePlan stage_plan(const BvhView& bv) {
   StagePlan s;
   s.bytes0 = STAGE == 2 ? bv.lane_bytes : (STAGE == 1 ? bv.nodes_bytes : 0u);
-  s.bytes1 = (COOP && STAGE >= 1) ? bv.boxes_bytes : 0u;
+  // The box tables of the cooperative search are never staged (render_coop_kernel reads everything through L1).
+  s.bytes1 = 0u;
   return s;
 }
 
@@ -342,17 +309,22 @@ __device__ __forceinline__ bool slab_test(const SlabRay& R, float best_f, float 
 //      three warp reductions on the bit pattern of t (monotonic: t_min < t <= +inf).
 // Shading then runs on all lanes redundantly (converged, one pass).  The set of objects tested is a superset of
 // the objects with a root (same padded boxes as the tree), so the hit is the lane mode's, bit for bit.
-template <int STAGE>
-__device__ __forceinline__ void coop_pixels(const BvhRenderParams& P, uint32_t coop_first, uint32_t coop_stride,
-                                         uint32_t n_coop) {
-  extern __shared__ __align__(128) uint8_t smem[];
+// Launched beside the lane kernel on its own high-priority stream (tor_api.cu); see CoopLayout for the placement.
+__global__ void __launch_bounds__(kCoopBlock, 1) render_coop_kernel(const __grid_constant__ BvhRenderParams P) {
+  const uint32_t warp = threadIdx.x >> 5;
+  if (warp >= kCoopWarps) return;  // the other warps only hold the SM's registers
+  const uint32_t n_coop = P.sched[0];
+  const uint32_t n_used = coop_ctas_used(P.coop, n_coop);
+  if (blockIdx.x >= n_used) return;
+  if (threadIdx.x == 0) atomicAdd(P.deal_ticket + 1, 1u);  // resident: coop_gate_kernel lets the lane kernel start
+  unsigned long long dbg_t0 = 0;
+  if (P.dbg_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
   const BvhView& bv = P.bv;
-  const double2* __restrict__ recs = reinterpret_cast<const double2*>((STAGE == 2 ? smem : P.blob) + bv.off_objs);
-  // the box tables sit behind the staged blob prefix (stage_plan)
-  const uint32_t box_base = STAGE >= 1 ? stage_plan<STAGE, true>(bv).bytes0 : bv.off_cboxes;
-  const float* __restrict__ cboxes = reinterpret_cast<const float*>((STAGE >= 1 ? smem : P.blob) + box_base);
-  const float* __restrict__ oboxes = cboxes + 6 * bv.ncl_pad;
-  const uint32_t cboxes_sa = smem_u32(smem) + box_base, oboxes_sa = cboxes_sa + 24u * (uint32_t)bv.ncl_pad;
+  // everything is read from global memory: the SM is this CTA's alone, its whole 256 KB is L1
+  const double2* __restrict__ recs = reinterpret_cast<const double2*>(P.blob + bv.off_objs);
+  const float* __restrict__ cboxes = reinterpret_cast<const float*>(P.blob + bv.off_cboxes);
+  const float* __restrict__ oboxes = reinterpret_cast<const float*>(P.blob + bv.off_oboxes);
+  const uint32_t cboxes_sa = 0u, oboxes_sa = 0u;
   Lane L;
   L.pix = v3(0, 0, 0);
   L.att = v3(1, 1, 1);
@@ -368,8 +340,13 @@ __device__ __forceinline__ void coop_pixels(const BvhRenderParams& P, uint32_t c
   uint32_t box_count = 0, test_count = 0;
   const int lane = threadIdx.x & 31;
   const int32_t n_always = bv.n_objects - bv.n_tree_objs;
-  // one pixel per warp in a real render; more only when a test forces more cooperative pixels than warps
-  for (uint32_t cr = coop_first; cr < n_coop; cr += coop_stride) {
+  // The cooperative pixels are a queue, most expensive first: a warp that finishes one takes the next, so the SMs
+  // that are set aside stay busy until the list is empty (there may be several times more pixels than warps).
+  for (;;) {
+    uint32_t cr = 0;
+    if (lane == 0) cr = atomicAdd(P.deal_ticket + 2, 1u);
+    cr = __shfl_sync(0xffffffffu, cr, 0);
+    if (cr >= n_coop) break;
     const uint32_t pid = P.coop_list[cr];
     {
       const int32_t ri = (int32_t)(pid / (uint32_t)P.ncols);
@@ -385,6 +362,9 @@ __device__ __forceinline__ void coop_pixels(const BvhRenderParams& P, uint32_t c
       for (;;) {  // render.nim:25-47, one bounce segment per pass
         if (lane == 0) ++seg_count;
         setup_ray(L.o, L.d, bv.s_limit, C, R);
+        // Metal, Dielectric and the sky need unit_vector(d) (a sqrt and a divide in a row): it does not depend on the
+        // hit, so it is issued here and completes while the lanes search (the warp has issue slots to spare)
+        const V3 ud = unit_vector(L.d);
         // Candidate records of this lane, kept in registers: a lane whose object box is entered in a cluster
         // round remembers the record, and the exact tests run afterwards, all lanes together.  Objects without a
         // finite box ("always" list: the ground sphere) start out as the candidates of the top lanes.  More
@@ -399,9 +379,9 @@ __device__ __forceinline__ void coop_pixels(const BvhRenderParams& P, uint32_t c
           const int32_t obj = cj * 32 + lane;
           const int32_t ob = cj * 192 + lane;
           const bool in =
-              slab_test(R, C.best_f, ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 32),
-                       ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 64), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 96),
-                       ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 128), ld4f<(STAGE >= 1)>(oboxes, oboxes_sa, ob + 160));
+              slab_test(R, C.best_f, ld4f<false>(oboxes, oboxes_sa, ob), ld4f<false>(oboxes, oboxes_sa, ob + 32),
+                       ld4f<false>(oboxes, oboxes_sa, ob + 64), ld4f<false>(oboxes, oboxes_sa, ob + 96),
+                       ld4f<false>(oboxes, oboxes_sa, ob + 128), ld4f<false>(oboxes, oboxes_sa, ob + 160));
           return (ci >= 0 && obj < bv.n_tree_objs && in) ? obj : -1;
         };
         auto remember = [&](int32_t obj) {
@@ -415,11 +395,11 @@ __device__ __forceinline__ void coop_pixels(const BvhRenderParams& P, uint32_t c
           const int32_t c = cb + lane;
           const int32_t cc = c < bv.n_clusters ? c : 0;  // padding lanes read cluster 0 and are masked out
           const bool h =
-              slab_test(R, C.best_f, ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, cc), ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, bv.ncl_pad + cc),
-                       ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 2 * bv.ncl_pad + cc),
-                       ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 3 * bv.ncl_pad + cc),
-                       ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 4 * bv.ncl_pad + cc),
-                       ld4f<(STAGE >= 1)>(cboxes, cboxes_sa, 5 * bv.ncl_pad + cc)) &&
+              slab_test(R, C.best_f, ld4f<false>(cboxes, cboxes_sa, cc), ld4f<false>(cboxes, cboxes_sa, bv.ncl_pad + cc),
+                       ld4f<false>(cboxes, cboxes_sa, 2 * bv.ncl_pad + cc),
+                       ld4f<false>(cboxes, cboxes_sa, 3 * bv.ncl_pad + cc),
+                       ld4f<false>(cboxes, cboxes_sa, 4 * bv.ncl_pad + cc),
+                       ld4f<false>(cboxes, cboxes_sa, 5 * bv.ncl_pad + cc)) &&
               c < bv.n_clusters;
           unsigned hit_clusters = __ballot_sync(0xffffffffu, h);
           if (lane == 0) box_count += 1u + (uint32_t)__popc(hit_clusters);
@@ -475,7 +455,7 @@ __device__ __forceinline__ void coop_pixels(const BvhRenderParams& P, uint32_t c
           C.best_t = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | (unsigned long long)mlo));
         }
         if (C.best_rec < 0) {
-          color = shade_miss(L);
+          color = shade_miss(L, &ud);
           break;
         }
         const double2* __restrict__ r = recs + kRecStride16 * C.best_rec;
@@ -487,7 +467,7 @@ __device__ __forceinline__ void coop_pixels(const BvhRenderParams& P, uint32_t c
         S.albedo = v3(a6.x, a6.y, a7.x);
         S.fuzz_or_ior = a7.y;
         S.mat_kind = (kind_mat >> 8) & 0xffu;
-        if (shade_hit(L, C.best_t, S, P.max_depth)) break;  // absorbed or depth exhausted: black
+        if (shade_hit(L, C.best_t, S, P.max_depth, &ud)) break;  // absorbed or depth exhausted: black
       }
       L.pix.x += color.x;  // render.nim:67
       L.pix.y += color.y;
@@ -500,6 +480,14 @@ __device__ __forceinline__ void coop_pixels(const BvhRenderParams& P, uint32_t c
       out[2] = L.pix.z;
     }
     __syncwarp();
+  }
+  if (P.dbg_times && lane == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    unsigned long long* e = P.dbg_times + 3ull * (blockIdx.x * kCoopWarps + warp);
+    e[0] = dbg_t0;
+    e[1] = t1;
+    e[2] = seg_count;
   }
   if (P.count_segments) {
     unsigned long long box_sum = box_count, test_sum = test_count;
@@ -516,7 +504,17 @@ __device__ __forceinline__ void coop_pixels(const BvhRenderParams& P, uint32_t c
   }
 }
 
-template <int BLOCK, int STAGE, bool CHUNKED, bool COOP>
+// Runs on the lane kernel's stream just before it: returns once the cooperative CTAs that have pixels are resident
+// on their SMs (or after ~1 ms, whatever happens: nothing depends on it but the placement).  Without it the lane
+// kernel's persistent grid can take every SM first, and the cooperative pixels — the longest chains of the launch —
+// would only start when the lanes run out of work.
+__global__ void coop_gate_kernel(const uint32_t* __restrict__ sched, const unsigned int* arrived, CoopLayout lay) {
+  const uint32_t n_used = coop_ctas_used(lay, sched[0]);
+  const long long t0 = clock64();
+  while (*(volatile const unsigned int*)arrived < n_used && clock64() - t0 < 2000000ll) __nanosleep(500);
+}
+
+template <int BLOCK, int STAGE, bool CHUNKED>
 __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_bvh_kernel(const __grid_constant__ BvhRenderParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t stage_bar;
@@ -525,7 +523,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   const BvhView& bv = P.bv;
   // Staged in shared memory: STAGE 2 = nodes + records, STAGE 1 = nodes, and in both cases the box tables of the
   // cooperative search behind them when the kernel has cooperative warps (stage_plan; coop_pixels uses the same).
-  const StagePlan stg = stage_plan<STAGE, COOP>(bv);
+  const StagePlan stg = stage_plan<STAGE>(bv);
   if (tid == 0) {
     mbar_init(&stage_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -550,6 +548,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   const double2* __restrict__ recs = reinterpret_cast<const double2*>((STAGE == 2 ? smem : P.blob) + bv.off_objs);
   const uint32_t nodes_sa = smem_u32(smem) + bv.off_nodes;  // meaningful for STAGE >= 1 only
 
+  __shared__ uint32_t cta_ticket;
   __shared__ unsigned long long warp_chunk[CHUNKED ? BLOCK / 32 : 1][2];  // [next, end) slots of each warp's chunk
   unsigned long long* const wchunk = warp_chunk[CHUNKED ? tid >> 5 : 0];
   if (CHUNKED && (tid & 31) == 0) wchunk[0] = wchunk[1] = 0ull;
@@ -560,31 +559,27 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   const unsigned long long total_px = (unsigned long long)P.nsel_rows * (unsigned long long)P.ncols;
   const unsigned long long total_units = total_px << P.sub_log2;
   // Layout of the cost-ranked order (see BvhRenderParams): [dealt: 32 per non-cooperative warp][queue]
-  const uint32_t n_coop = (COOP && P.sched) ? P.sched[0] : 0u;  // cooperative pixels
-  WarpRole role;
-  if (COOP) {
-    role = warp_role(P.coop, n_coop, blockIdx.x, (uint32_t)(tid >> 5));
-  } else {  // no cooperative pixels: every warp is dealt its 32 entries
-    role.coop_first = 0xffffffffu;
-    role.coop_stride = 1u;
-    role.coop_cta = false;
-    role.deal_rank = (uint32_t)(tid >> 5) * gridDim.x + blockIdx.x;
+  unsigned long long dbg_t0 = 0;
+  if (P.dbg_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  const uint32_t n_coop = P.sched ? P.sched[0] : 0u;  // pixels render_coop_kernel traces
+  const unsigned long long grid_warps = (unsigned long long)gridDim.x * (unsigned long long)(BLOCK / 32);
+  // Dealing rank of this warp.  With cooperative pixels some of this grid's CTAs start late (their SMs are held by
+  // render_coop_kernel), so the ranks go out in arrival order: the CTAs that start at once share the dealt pixels.
+  uint32_t deal_rank = (uint32_t)(tid >> 5) * gridDim.x + blockIdx.x;
+  uint32_t n_deal_warps = gridDim.x * (uint32_t)(BLOCK / 32);
+  if (P.sched) {
+    if (tid == 0) cta_ticket = atomicAdd(P.deal_ticket, 1u);
+    __syncthreads();
+    n_deal_warps = deal_warps(P.coop, n_coop);
+    deal_rank = cta_ticket * (uint32_t)(BLOCK / 32) + (uint32_t)(tid >> 5);
+    if (deal_rank >= n_deal_warps) deal_rank = 0xffffffffu;
   }
-  const uint32_t first_wave =
-      P.first_wave ? (COOP ? deal_warps(P.coop, n_coop) : gridDim.x * (uint32_t)(BLOCK / 32)) * 32u : 0u;
+  const uint32_t first_wave = P.first_wave ? n_deal_warps * 32u : 0u;
   const uint32_t n_ranked = (uint32_t)total_px - n_coop;  // pixels that go to single lanes
   // length of the shared queue: everything, or what the cost-ranked order leaves after the dealt first wave
   const unsigned long long queue_len =
       P.order ? (unsigned long long)(n_ranked - (n_ranked < first_wave ? n_ranked : first_wave)) : total_units;
   const int refill = P.refill;
-
-  // ================================================================= warp-cooperative pixels (coop_pixels above)
-  // Called before any lane state exists, so that the call keeps nothing alive across it.
-  if constexpr (COOP) {
-    if (role.coop_first != 0xffffffffu) coop_pixels<STAGE>(P, role.coop_first, role.coop_stride, n_coop);  // warp-uniform
-    // An SM set aside for cooperative warps (CoopLayout mode 1): its other warps take no work until those are done.
-    if (role.coop_cta) asm volatile("bar.sync 1, %0;" ::"n"(BLOCK) : "memory");
-  }
 
   Lane L;
   L.pix = v3(0, 0, 0);
@@ -596,7 +591,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   uint32_t pid = 0;      // work unit: pixel index inside the selected rows (<< sub_log2 | sample range)
   uint32_t pix_seg = 0;  // bounce segments of the current unit
   bool active = false, need_pixel = (tid & 31) < P.lanes_per_warp, need_sample = false;
-  bool first_fetch = P.first_wave != 0 && role.deal_rank != 0xffffffffu;  // warps that are dealt nothing go straight to the queue
+  bool first_fetch = P.first_wave != 0 && deal_rank != 0xffffffffu;  // warps that are dealt nothing go straight to the queue
   bool trav_done = false;  // the current segment's closest hit is final
   bool need_setup = false;  // a new segment needs its traversal state
   unsigned long long seg_count = 0, ray_count = 0;
@@ -657,20 +652,30 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
       V3 color = v3(0, 0, 0);
       if (P.max_depth <= 0) {  // render.nim:25 — the bounce loop body never runs
         sample_done = true;
-      } else if (++seg_count, ++pix_seg, C.best_rec >= 0) {
-        const double2* __restrict__ r = recs + kRecStride16 * C.best_rec;
-        const double2 a2 = r[2], a6 = r[6], a7 = r[7];
-        const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
-        Surface S;
-        S.center = rec_center(r, kind_mat, L.time, C.qc);  // moving_spheres.nim:61
-        S.inv_r = a2.y;
-        S.albedo = v3(a6.x, a6.y, a7.x);
-        S.fuzz_or_ior = a7.y;
-        S.mat_kind = (kind_mat >> 8) & 0xffu;
-        sample_done = shade_hit(L, C.best_t, S, P.max_depth);
       } else {
-        color = shade_miss(L);
-        sample_done = true;
+        ++seg_count;
+        ++pix_seg;
+        const bool hit = C.best_rec >= 0;
+        const double2* __restrict__ r = recs + kRecStride16 * (hit ? C.best_rec : 0);
+        const double2 a2 = r[2];
+        const uint32_t kind_mat = (uint32_t)__double_as_longlong(a2.x);
+        const uint32_t mat_kind = (kind_mat >> 8) & 0xffu;
+        // unit_vector(d) once for every lane that needs it (Metal, Dielectric, sky) instead of once per branch
+        V3 ud = v3(0, 0, 0);
+        if (!hit || mat_kind != TOR_LAMBERTIAN) ud = unit_vector(L.d);
+        if (hit) {
+          const double2 a6 = r[6], a7 = r[7];
+          Surface S;
+          S.center = rec_center(r, kind_mat, L.time, C.qc);  // moving_spheres.nim:61
+          S.inv_r = a2.y;
+          S.albedo = v3(a6.x, a6.y, a7.x);
+          S.fuzz_or_ior = a7.y;
+          S.mat_kind = mat_kind;
+          sample_done = shade_hit(L, C.best_t, S, P.max_depth, &ud);
+        } else {
+          color = shade_miss(L, &ud);
+          sample_done = true;
+        }
       }
       need_setup = !sample_done;
       if (sample_done) {
@@ -705,8 +710,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
         for (;;) {
           if (first_fetch) {  // dealt pixel of this lane, if any
             first_fetch = false;
-            const uint32_t gid = role.deal_rank * 32u + (uint32_t)(tid & 31);
-            pid = (role.deal_rank != 0xffffffffu && gid < first_wave) ? P.order[gid] : 0xffffffffu;
+            const uint32_t gid = deal_rank * 32u + (uint32_t)(tid & 31);
+            pid = (deal_rank != 0xffffffffu && gid < first_wave) ? P.order[gid] : 0xffffffffu;
             if (pid == 0xffffffffu) continue;
           } else if (P.first_wave) {
             const unsigned long long slot = atomicAdd(P.work_counter, 1ull);
@@ -727,8 +732,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
       // the same few materials.  Warp-uniform loop: each pass hands one slot to every lane that still needs one.
       if (first_fetch) {  // cost-ranked order: the pixel dealt to this lane, if any
         first_fetch = false;
-        const uint32_t gid = role.deal_rank * 32u + (uint32_t)(tid & 31);
-        pid = (need_pixel && role.deal_rank != 0xffffffffu && gid < first_wave) ? P.order[gid] : 0xffffffffu;
+        const uint32_t gid = deal_rank * 32u + (uint32_t)(tid & 31);
+        pid = (need_pixel && deal_rank != 0xffffffffu && gid < first_wave) ? P.order[gid] : 0xffffffffu;
         if (pid != 0xffffffffu) need_pixel = !begin_unit();
       }
       for (;;) {
@@ -741,7 +746,14 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
           unsigned long long next = wchunk[0], end = wchunk[1];
           if (next >= end) {  // chunk used up: take the next one (short chunks near the end of the queue)
             const unsigned long long head = *(volatile unsigned long long*)P.work_counter;
-            const unsigned long long ch = head + P.chunk_guard < queue_len ? (unsigned long long)P.chunk : 32ull;
+            unsigned long long ch = head + P.chunk_guard < queue_len ? (unsigned long long)P.chunk : 32ull;
+            if (P.order && P.endgame_min_chunk) {
+              // cost-ranked queue with about one pixel per lane left: hand out what remains in equal shares, so that
+              // the render does not end on the warps that happened to get a whole chunk of 32 while others got none
+              const unsigned long long left = head < queue_len ? queue_len - head : 0ull;
+              const unsigned long long share = (left + grid_warps - 1ull) / grid_warps;
+              if (share < ch) ch = share < P.endgame_min_chunk ? (unsigned long long)P.endgame_min_chunk : share;
+            }
             next = atomicAdd(P.work_counter, ch);
             end = next + ch < queue_len ? next + ch : queue_len;
             if (next > end) next = end;
@@ -873,6 +885,13 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
     __syncwarp();
   }
 
+  if (P.dbg_times && (tid & 31) == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    unsigned long long* e = P.dbg_times + 3ull * 4096ull + 2ull * (blockIdx.x * (BLOCK / 32) + (tid >> 5));
+    e[0] = dbg_t0;
+    e[1] = t1;
+  }
   if (P.count_segments) {
     unsigned long long box_sum = box_count, test_sum = test_count;
     for (int ofs = 16; ofs > 0; ofs >>= 1) {
