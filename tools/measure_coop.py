@@ -34,10 +34,10 @@ def main():
     if QUICK:
         settings.append(("default", {}))
     else:
-        for eg in (0, 1, 4, 8, 16):
-            settings.append((f"a1_endgame{eg}", {"TOR_BVH_COOP_ALPHA": 1, "TOR_BVH_ENDGAME": eg}))
-        settings.append(("a1_eg4_max15", {"TOR_BVH_COOP_ALPHA": 1, "TOR_BVH_ENDGAME": 4, "TOR_BVH_COOP_MAX": 15}))
-        settings.append(("a1_eg4_nodeal", {"TOR_BVH_COOP_ALPHA": 1, "TOR_BVH_ENDGAME": 4, "TOR_BVH_EXACT_DEAL": 0}))
+        settings.append(("default", {}))
+        for lanes in (24, 16, 8):
+            settings.append((f"thin{lanes}", {"TOR_BVH_THIN_PXLANE": 400, "TOR_BVH_THIN_LANES": lanes}))
+        settings.append(("thin16_max25", {"TOR_BVH_THIN_PXLANE": 400, "TOR_BVH_THIN_LANES": 16, "TOR_BVH_COOP_MAX": 25}))
     out = {}
     for name, env in settings:
         ctx = ctx_with(env)

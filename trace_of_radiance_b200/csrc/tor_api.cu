@@ -45,6 +45,8 @@ struct Tuning {
                                //   cooperatively (tests), still capped by coop_max_pct
   int prepass_min_spp = 256;   // TOR_BVH_PREPASS_SPP: samples per pixel from which the cost pre-pass runs
   int coop_px_per_lane = 8;    // TOR_BVH_COOP_PXLANE: cooperative pixels only when the launch has fewer pixels per lane
+  int thin_px_per_lane = 0;    // TOR_BVH_THIN_PXLANE: launches with fewer pixels per lane than this / 100 run `thin_lanes`
+  int thin_lanes = 16;         // TOR_BVH_THIN_LANES: lanes per warp of the dealt wave (0 = never)
   int endgame_min_chunk = 4;   // TOR_BVH_ENDGAME: smallest share of the cost-ranked queue a warp takes near the end (0: off)
   int coop_queue_factor = 4;   // TOR_BVH_COOP_QUEUE: at most this many cooperative pixels per cooperative warp
   bool debug_times = false;    // TOR_BVH_DEBUG_TIMES: record start / end stamps of every warp (tor_debug_times)
@@ -86,6 +88,8 @@ struct Tuning {
     t.coop_px_per_lane = clampi(geti("TOR_BVH_COOP_PXLANE", 8), 0, 1 << 20);
     t.coop_queue_factor = clampi(geti("TOR_BVH_COOP_QUEUE", 4), 1, 64);
     t.endgame_min_chunk = clampi(geti("TOR_BVH_ENDGAME", 4), 0, 32);
+    t.thin_px_per_lane = clampi(geti("TOR_BVH_THIN_PXLANE", 0), 0, 100000);
+    t.thin_lanes = clampi(geti("TOR_BVH_THIN_LANES", 16), 1, 32);
     t.stage_max = clampi(geti("TOR_BVH_STAGE", 2), 0, 2);
     t.anim_grid_divisor = clampi(geti("TOR_ANIM_GRID_DIV", 0), 0, 64);
     t.debug_times = getenv("TOR_BVH_DEBUG_TIMES") != nullptr;
@@ -509,7 +513,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       P.refill = tune.refill_fast < P.lanes_per_warp ? tune.refill_fast : P.lanes_per_warp;
     }
     if (P.refill < 1) P.refill = 1;
-    if (reorder && pre > 0 && P.lanes_per_warp == 32 && (block % 32) == 0) {
+    if (reorder && pre > 0 && (block % 32) == 0) {
       const uint32_t warps_all = (uint32_t)(lanes / 32);
       const uint32_t warps = tune.deal ? warps_all : 0u;  // warps that are dealt a first wave
       const uint32_t n = (uint32_t)total_px;
@@ -536,6 +540,15 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       lay.wpc = (uint32_t)(block / 32);
       lay.per_sm = (uint32_t)per_sm;
       lay.coop_grid = 0;
+      // With about one pixel per lane the warps need not be full: fewer active lanes per warp trace each pixel faster
+      // (9.6 us per segment per lane in a full warp, 6.3 with 16 lanes) at a throughput that nobody needs then.
+      // The dealt wave hands lanes 0 .. L-1 of every warp a pixel (L a multiple of the dealing group).
+      if (tune.lanes == 32 && tune.thin_px_per_lane > 0 &&
+          total_px * 100ull < lanes * (unsigned long long)tune.thin_px_per_lane)
+        P.lanes_per_warp = tune.thin_lanes;
+      if (P.lanes_per_warp % tune.deal_group) P.lanes_per_warp = std::max(tune.deal_group, P.lanes_per_warp / tune.deal_group * tune.deal_group);
+      if (P.refill > (P.lanes_per_warp * 5) / 8) P.refill = std::max(1, (P.lanes_per_warp * 5) / 8);
+      lay.lanes = (uint32_t)P.lanes_per_warp;
       // Only launches with few pixels per lane can end on a single pixel's chain (C2: a GPU's share in a 4- or
       // 8-GPU render); with many pixels per lane the dealt first wave hides the chains and the SMs are better used
       // by the lanes.  Cooperative CTAs take whole SMs, so the grid must be the full persistent one.
@@ -559,6 +572,8 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       Q.work_counter = d.d_work + 1;
       Q.cost = d.d_cost;
       Q.scramble = coprime_near_golden(n);
+      Q.lanes_per_warp = tune.lanes;  // the pre-pass is throughput work: full warps
+      Q.refill = std::max(1, std::min(tune.refill, (tune.lanes * 5) / 8));
       plan.fn<<<grid, block, plan.smem, stream>>>(Q);
       TOR_CUDA(ctx, cudaGetLastError());
       TOR_CUDA(ctx, cudaMemsetAsync(d.d_hist, 0, tor::kCostBuckets * sizeof(uint32_t), stream));

@@ -41,6 +41,8 @@ struct CoopLayout {
   uint32_t coop_grid;  // CTAs of the cooperative kernel (0: no cooperative pixels in this launch)
   uint32_t grid, wpc;  // lane kernel: CTAs and warps per CTA
   uint32_t per_sm;     // lane-kernel CTAs that one cooperative CTA keeps off its SM
+  uint32_t lanes;      // lanes of each warp that take pixels (BvhRenderParams::lanes_per_warp): the dealt wave gives a
+                       // warp `lanes` pixels; its slots in `order` stay 32 apart
 };
 // cooperative CTAs that get pixels when K pixels are cooperative
 __host__ __device__ __forceinline__ uint32_t coop_ctas_used(const CoopLayout& c, uint32_t K) {
@@ -521,8 +523,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
 
   const int tid = threadIdx.x;
   const BvhView& bv = P.bv;
-  // Staged in shared memory: STAGE 2 = nodes + records, STAGE 1 = nodes, and in both cases the box tables of the
-  // cooperative search behind them when the kernel has cooperative warps (stage_plan; coop_pixels uses the same).
+  // Staged in shared memory: STAGE 2 = nodes + records, STAGE 1 = nodes (stage_plan); the rest comes through L1.
   const StagePlan stg = stage_plan<STAGE>(bv);
   if (tid == 0) {
     mbar_init(&stage_bar, 1);
@@ -577,8 +578,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   const uint32_t first_wave = P.first_wave ? n_deal_warps * 32u : 0u;
   const uint32_t n_ranked = (uint32_t)total_px - n_coop;  // pixels that go to single lanes
   // length of the shared queue: everything, or what the cost-ranked order leaves after the dealt first wave
+  const uint32_t n_dealt_cap = P.first_wave ? n_deal_warps * (uint32_t)P.lanes_per_warp : 0u;  // pixels the dealt wave holds
   const unsigned long long queue_len =
-      P.order ? (unsigned long long)(n_ranked - (n_ranked < first_wave ? n_ranked : first_wave)) : total_units;
+      P.order ? (unsigned long long)(n_ranked - (n_ranked < n_dealt_cap ? n_ranked : n_dealt_cap)) : total_units;
   const int refill = P.refill;
 
   Lane L;
@@ -1025,7 +1027,8 @@ __device__ __forceinline__ RankLayout rank_layout(const uint32_t* __restrict__ s
   r.first_wave = r.warps * 32u;
   r.tier = r.warps * group;
   const uint32_t n_ranked = n - r.n_coop;
-  r.n_first = n_ranked < r.first_wave ? n_ranked : r.first_wave;
+  const uint32_t cap = r.warps * (coop.lanes ? coop.lanes : 32u);  // tiers fill lanes 0 .. lanes-1 of every warp
+  r.n_first = n_ranked < cap ? n_ranked : cap;
   return r;
 }
 __device__ __forceinline__ void place_rank(const RankLayout& r, uint32_t pos, uint32_t pixel, uint32_t group,
