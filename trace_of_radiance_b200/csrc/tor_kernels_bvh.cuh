@@ -364,9 +364,6 @@ __global__ void __launch_bounds__(kCoopBlock, 1) render_coop_kernel(const __grid
       for (;;) {  // render.nim:25-47, one bounce segment per pass
         if (lane == 0) ++seg_count;
         setup_ray(L.o, L.d, bv.s_limit, C, R);
-        // Metal, Dielectric and the sky need unit_vector(d) (a sqrt and a divide in a row): it does not depend on the
-        // hit, so it is issued here and completes while the lanes search (the warp has issue slots to spare)
-        const V3 ud = unit_vector(L.d);
         // Candidate records of this lane, kept in registers: a lane whose object box is entered in a cluster
         // round remembers the record, and the exact tests run afterwards, all lanes together.  Objects without a
         // finite box ("always" list: the ground sphere) start out as the candidates of the top lanes.  More
@@ -457,7 +454,7 @@ __global__ void __launch_bounds__(kCoopBlock, 1) render_coop_kernel(const __grid
           C.best_t = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | (unsigned long long)mlo));
         }
         if (C.best_rec < 0) {
-          color = shade_miss(L, &ud);
+          color = shade_miss(L);
           break;
         }
         const double2* __restrict__ r = recs + kRecStride16 * C.best_rec;
@@ -469,7 +466,7 @@ __global__ void __launch_bounds__(kCoopBlock, 1) render_coop_kernel(const __grid
         S.albedo = v3(a6.x, a6.y, a7.x);
         S.fuzz_or_ior = a7.y;
         S.mat_kind = (kind_mat >> 8) & 0xffu;
-        if (shade_hit(L, C.best_t, S, P.max_depth, &ud)) break;  // absorbed or depth exhausted: black
+        if (shade_hit(L, C.best_t, S, P.max_depth)) break;  // absorbed or depth exhausted: black
       }
       L.pix.x += color.x;  // render.nim:67
       L.pix.y += color.y;
