@@ -35,9 +35,8 @@ def main():
         settings.append(("default", {}))
     else:
         settings.append(("default", {}))
-        for lanes in (24, 16, 8):
-            settings.append((f"thin{lanes}", {"TOR_BVH_THIN_PXLANE": 400, "TOR_BVH_THIN_LANES": lanes}))
-        settings.append(("thin16_max25", {"TOR_BVH_THIN_PXLANE": 400, "TOR_BVH_THIN_LANES": 16, "TOR_BVH_COOP_MAX": 25}))
+        for cw, mx in ((4, 15), (4, 30), (16, 15), (16, 8), (12, 15), (6, 20)):
+            settings.append((f"cw{cw}_max{mx}", {"TOR_BVH_COOP_WARPS": cw, "TOR_BVH_COOP_MAX": mx}))
     out = {}
     for name, env in settings:
         ctx = ctx_with(env)

@@ -31,14 +31,17 @@ namespace tor {
 
 // Cooperative pixels run in their OWN kernel (render_coop_kernel below): one CTA of 512 threads per SM that is set
 // aside — with 128 registers per thread such a CTA takes the SM's whole register file, so no CTA of the lane kernel can
-// share the SM, and only kCoopWarps of its warps (two per scheduler) do any work: a cooperative warp is a serial
-// dependency chain and every other warp on its scheduler takes issue slots from it.  The lane kernel is launched with
-// its usual grid; its CTAs that find no SM free start when the cooperative CTAs are done and go straight to the
-// queue.  CoopLayout tells both kernels and the scatter kernels how the ranked pixels are laid out.
-static constexpr uint32_t kCoopWarps = 8;    // working warps per cooperative CTA
+// share the SM: a cooperative warp is a serial dependency chain, and the hundreds of lanes of a lane CTA on the same
+// schedulers would take most of its issue slots.  `cw` of the CTA's 16 warps work (all 16 by default: a warp alone on
+// its SM needs 1.0 us per segment, sixteen need 2.3 us each but deliver three times the pixels per SM, and the SMs
+// set aside are what the lanes lose).  The lane kernel is launched with its usual grid; its CTAs that find no SM free
+// start when cooperative CTAs are done and go straight to the queue.  CoopLayout tells both kernels and the scatter
+// kernels how the ranked pixels are laid out.
+static constexpr uint32_t kCoopWarps = 16;   // working warps per cooperative CTA (default; CoopLayout::cw)
 static constexpr uint32_t kCoopBlock = 512;  // threads per cooperative CTA (fills an SM's register file)
 struct CoopLayout {
   uint32_t coop_grid;  // CTAs of the cooperative kernel (0: no cooperative pixels in this launch)
+  uint32_t cw;         // working warps per cooperative CTA (default kCoopWarps; the rest only hold the registers)
   uint32_t grid, wpc;  // lane kernel: CTAs and warps per CTA
   uint32_t per_sm;     // lane-kernel CTAs that one cooperative CTA keeps off its SM
   uint32_t lanes;      // lanes of each warp that take pixels (BvhRenderParams::lanes_per_warp): the dealt wave gives a
@@ -46,7 +49,7 @@ struct CoopLayout {
 };
 // cooperative CTAs that get pixels when K pixels are cooperative
 __host__ __device__ __forceinline__ uint32_t coop_ctas_used(const CoopLayout& c, uint32_t K) {
-  const uint32_t want = (K + kCoopWarps - 1u) / kCoopWarps;
+  const uint32_t want = (K + c.cw - 1u) / c.cw;
   return want < c.coop_grid ? want : c.coop_grid;
 }
 // warps of the lane kernel that are dealt pixels: those of the CTAs that start at once
@@ -314,7 +317,7 @@ __device__ __forceinline__ bool slab_test(const SlabRay& R, float best_f, float 
 // Launched beside the lane kernel on its own high-priority stream (tor_api.cu); see CoopLayout for the placement.
 __global__ void __launch_bounds__(kCoopBlock, 1) render_coop_kernel(const __grid_constant__ BvhRenderParams P) {
   const uint32_t warp = threadIdx.x >> 5;
-  if (warp >= kCoopWarps) return;  // the other warps only hold the SM's registers
+  if (warp >= P.coop.cw) return;  // the other warps only hold the SM's registers
   const uint32_t n_coop = P.sched[0];
   const uint32_t n_used = coop_ctas_used(P.coop, n_coop);
   if (blockIdx.x >= n_used) return;
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(kCoopBlock, 1) render_coop_kernel(const __grid
   if (P.dbg_times && lane == 0) {
     unsigned long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    unsigned long long* e = P.dbg_times + 3ull * (blockIdx.x * kCoopWarps + warp);
+    unsigned long long* e = P.dbg_times + 3ull * (blockIdx.x * P.coop.cw + warp);
     e[0] = dbg_t0;
     e[1] = t1;
     e[2] = seg_count;
