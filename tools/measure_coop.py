@@ -34,9 +34,9 @@ def main():
     if QUICK:
         settings.append(("default", {}))
     else:
-        settings.append(("default", {}))
-        for cw, mx in ((4, 15), (4, 30), (16, 15), (16, 8), (12, 15), (6, 20)):
-            settings.append((f"cw{cw}_max{mx}", {"TOR_BVH_COOP_WARPS": cw, "TOR_BVH_COOP_MAX": mx}))
+        for fast, fw, mx in ((0, 8, 15), (50, 8, 15), (50, 4, 15), (30, 4, 15), (70, 8, 15), (50, 8, 20), (100, 8, 20), (50, 6, 18)):
+            settings.append((f"fast{fast}_fw{fw}_max{mx}", {"TOR_BVH_COOP_FAST": fast, "TOR_BVH_COOP_FAST_WARPS": fw,
+                                                            "TOR_BVH_COOP_MAX": mx}))
     out = {}
     for name, env in settings:
         ctx = ctx_with(env)

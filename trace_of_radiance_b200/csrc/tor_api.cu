@@ -47,6 +47,10 @@ struct Tuning {
   int coop_px_per_lane = 8;    // TOR_BVH_COOP_PXLANE: cooperative pixels only when the launch has fewer pixels per lane
   int thin_px_per_lane = 0;    // TOR_BVH_THIN_PXLANE: launches with fewer pixels per lane than this / 100 run `thin_lanes`
   int thin_lanes = 16;         // TOR_BVH_THIN_LANES: lanes per warp of the dealt wave (0 = never)
+  int coop_fast_pct = 0;       // TOR_BVH_COOP_FAST: this percentage of the cooperative CTAs runs only coop_fast_warps warps
+  int coop_fast_warps = 8;     // TOR_BVH_COOP_FAST_WARPS: ... and starts on the most expensive pixels of the launch (off by
+                               //   default: measured 46-57 ms against 41 on a GPU's share of C2 on 8 GPUs — the set-aside
+                               //   SMs are throughput-bound, not bound by their longest chain)
   int coop_warps = 16;         // TOR_BVH_COOP_WARPS: working warps per cooperative CTA (1 .. 16)
   int endgame_min_chunk = 4;   // TOR_BVH_ENDGAME: smallest share of the cost-ranked queue a warp takes near the end (0: off)
   int coop_queue_factor = 4;   // TOR_BVH_COOP_QUEUE: at most this many cooperative pixels per cooperative warp
@@ -90,6 +94,8 @@ struct Tuning {
     t.coop_queue_factor = clampi(geti("TOR_BVH_COOP_QUEUE", 4), 1, 64);
     t.endgame_min_chunk = clampi(geti("TOR_BVH_ENDGAME", 4), 0, 32);
     t.coop_warps = clampi(geti("TOR_BVH_COOP_WARPS", (int)tor::kCoopWarps), 1, 16);
+    t.coop_fast_pct = clampi(geti("TOR_BVH_COOP_FAST", 0), 0, 100);
+    t.coop_fast_warps = clampi(geti("TOR_BVH_COOP_FAST_WARPS", 8), 1, 16);
     t.thin_px_per_lane = clampi(geti("TOR_BVH_THIN_PXLANE", 0), 0, 100000);
     t.thin_lanes = clampi(geti("TOR_BVH_THIN_LANES", 16), 1, 32);
     t.stage_max = clampi(geti("TOR_BVH_STAGE", 2), 0, 2);
@@ -543,6 +549,8 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       lay.per_sm = (uint32_t)per_sm;
       lay.coop_grid = 0;
       lay.cw = (uint32_t)tune.coop_warps;
+      lay.n_fast = 0;
+      lay.cw_fast = (uint32_t)std::min(tune.coop_fast_warps, tune.coop_warps);
       // With about one pixel per lane the warps need not be full: fewer active lanes per warp trace each pixel faster
       // (9.6 us per segment per lane in a full warp, 6.3 with 16 lanes) at a throughput that nobody needs then.
       // The dealt wave hands lanes 0 .. L-1 of every warp a pixel (L a multiple of the dealing group).
@@ -559,6 +567,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       const bool full_grid = grid == per_sm * d.sm_count;
       if (coherent && warps && tune.coop_max_pct > 0 && ((few_pixels && full_grid) || tune.coop_force >= 0)) {
         lay.coop_grid = std::max(1u, (uint32_t)((unsigned long long)d.sm_count * (unsigned)tune.coop_max_pct / 100ull));
+        lay.n_fast = (uint32_t)((unsigned long long)lay.coop_grid * (unsigned)tune.coop_fast_pct / 100ull);
         coop_max = lay.coop_grid * lay.cw * (uint32_t)tune.coop_queue_factor;  // a queue: several per warp
         if (tune.coop_force >= 0) coop_max = n;  // tests: any number of pixels, the warps loop
       }

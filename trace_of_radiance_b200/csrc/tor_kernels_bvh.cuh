@@ -42,6 +42,9 @@ static constexpr uint32_t kCoopBlock = 512;  // threads per cooperative CTA (fil
 struct CoopLayout {
   uint32_t coop_grid;  // CTAs of the cooperative kernel (0: no cooperative pixels in this launch)
   uint32_t cw;         // working warps per cooperative CTA (default kCoopWarps; the rest only hold the registers)
+  uint32_t n_fast, cw_fast;  // the first n_fast CTAs run only cw_fast warps and start on the cw_fast * n_fast most
+                             // expensive pixels (pixel k -> CTA k mod n_fast): the longest chains of the launch get
+                             // SMs with few neighbours; everything else comes from the shared queue
   uint32_t grid, wpc;  // lane kernel: CTAs and warps per CTA
   uint32_t per_sm;     // lane-kernel CTAs that one cooperative CTA keeps off its SM
   uint32_t lanes;      // lanes of each warp that take pixels (BvhRenderParams::lanes_per_warp): the dealt wave gives a
@@ -49,7 +52,13 @@ struct CoopLayout {
 };
 // cooperative CTAs that get pixels when K pixels are cooperative
 __host__ __device__ __forceinline__ uint32_t coop_ctas_used(const CoopLayout& c, uint32_t K) {
-  const uint32_t want = (K + c.cw - 1u) / c.cw;
+  const uint32_t head = c.n_fast * c.cw_fast;  // pixels the fast CTAs start on
+  uint32_t want;
+  if (K <= head) {
+    want = K < c.n_fast ? K : c.n_fast;
+  } else {
+    want = c.n_fast + (K - head + c.cw - 1u) / c.cw;
+  }
   return want < c.coop_grid ? want : c.coop_grid;
 }
 // warps of the lane kernel that are dealt pixels: those of the CTAs that start at once
@@ -317,10 +326,13 @@ __device__ __forceinline__ bool slab_test(const SlabRay& R, float best_f, float 
 // Launched beside the lane kernel on its own high-priority stream (tor_api.cu); see CoopLayout for the placement.
 __global__ void __launch_bounds__(kCoopBlock, 1) render_coop_kernel(const __grid_constant__ BvhRenderParams P) {
   const uint32_t warp = threadIdx.x >> 5;
-  if (warp >= P.coop.cw) return;  // the other warps only hold the SM's registers
+  const bool fast_cta = blockIdx.x < P.coop.n_fast;
+  if (warp >= (fast_cta ? P.coop.cw_fast : P.coop.cw)) return;  // the other warps only hold the SM's registers
   const uint32_t n_coop = P.sched[0];
   const uint32_t n_used = coop_ctas_used(P.coop, n_coop);
   if (blockIdx.x >= n_used) return;
+  // first pixel of a fast CTA's warp: fixed (the head of the ranking, spread over the fast CTAs)
+  uint32_t first_px = fast_cta ? warp * P.coop.n_fast + blockIdx.x : 0xffffffffu;
   if (threadIdx.x == 0) atomicAdd(P.deal_ticket + 1, 1u);  // resident: coop_gate_kernel lets the lane kernel start
   unsigned long long dbg_t0 = 0;
   if (P.dbg_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
@@ -348,10 +360,16 @@ __global__ void __launch_bounds__(kCoopBlock, 1) render_coop_kernel(const __grid
   // The cooperative pixels are a queue, most expensive first: a warp that finishes one takes the next, so the SMs
   // that are set aside stay busy until the list is empty (there may be several times more pixels than warps).
   for (;;) {
-    uint32_t cr = 0;
-    if (lane == 0) cr = atomicAdd(P.deal_ticket + 2, 1u);
-    cr = __shfl_sync(0xffffffffu, cr, 0);
-    if (cr >= n_coop) break;
+    uint32_t cr = first_px;
+    first_px = 0xffffffffu;
+    if (cr == 0xffffffffu) {  // the shared queue starts behind the fast CTAs' first pixels
+      if (lane == 0) cr = P.coop.n_fast * P.coop.cw_fast + atomicAdd(P.deal_ticket + 2, 1u);
+      cr = __shfl_sync(0xffffffffu, cr, 0);
+    }
+    if (cr >= n_coop) {
+      if (cr < P.coop.n_fast * P.coop.cw_fast) continue;  // a fast warp without a first pixel: on to the queue
+      break;
+    }
     const uint32_t pid = P.coop_list[cr];
     {
       const int32_t ri = (int32_t)(pid / (uint32_t)P.ncols);
