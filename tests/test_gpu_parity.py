@@ -390,18 +390,56 @@ def test_cooperative_pixels_c1_digest(tor):
 
 
 def test_cooperative_pixels_default_policy_on_a_gpu_share_of_c2(tor, oracle, gpu_ctx):
-    """An eighth of C2's rows (one GPU's share of an 8-GPU render) with the default policy — the cost pre-pass picks
-    the cooperative pixels itself — against the same rows of the brute-force scan, and one row against the oracle."""
+    """An eighth and a half of C2's rows (one GPU's share of an 8- and of a 2-GPU render) with the default policy —
+    the cost pre-pass picks the cooperative pixels itself, and the tail of the launch is handed to one warp per pixel —
+    against the same rows through the plain row-major pixel queue, and one row against the oracle."""
     world, cam = tor.random_scene().list(), _book_cam(tor)
     h, w, spp = 675, 1200, 500
-    a = tor.newCanvas(h, w, spp, 2.2)
-    b = tor.newCanvas(h, w, spp, 2.2)
-    gpu_ctx.render(a, cam, world, 50, rows=(3, h, 8))
-    gpu_ctx.render(b, cam, world, 50, rows=(3, h, 8), flags=tor.api.TOR_FLAG_ROW_MAJOR_QUEUE)
-    assert a.pixels.tobytes() == b.pixels.tobytes()
+    for first, step in ((3, 8), (1, 2)):
+        a = tor.newCanvas(h, w, spp, 2.2)
+        b = tor.newCanvas(h, w, spp, 2.2)
+        gpu_ctx.render(a, cam, world, 50, rows=(first, h, step))
+        assert gpu_ctx.last_schedule()["cooperative_pixels"] > 0
+        parked = gpu_ctx.last_handoffs()
+        assert parked["from_lanes"] + parked["from_cooperative_warps"] > 0, parked
+        gpu_ctx.render(b, cam, world, 50, rows=(first, h, step), flags=tor.api.TOR_FLAG_ROW_MAJOR_QUEUE)
+        assert a.pixels.tobytes() == b.pixels.tobytes(), step
     ref = np.zeros((h, w, 3))
     oracle.render(h, w, spp, cam.as_array(), world.objects, rows=(203, 204, 1), math="det", out=ref)
     assert a.pixels[203].tobytes() == ref[203].tobytes()
+
+
+# ---------------------------------------------------------------------------------- late hand-off
+@pytest.mark.parametrize("env", [
+    dict(TOR_BVH_HANDOFF=1, TOR_BVH_HANDOFF_MIN_LEFT=1),                          # tail flag up at once: parked at sample 0 or 1
+    dict(TOR_BVH_HANDOFF=1, TOR_BVH_HANDOFF_MIN_LEFT=4, TOR_BVH_COOP_FORCE=10 ** 9),  # every pixel cooperative: parked by those warps
+    dict(TOR_BVH_HANDOFF=93, TOR_BVH_HANDOFF_MIN_LEFT=2),                         # flag goes up while pixels are in flight
+    dict(TOR_BVH_HANDOFF=93, TOR_BVH_HANDOFF_MIN_LEFT=2, TOR_BVH_COOP_FORCE=300, TOR_BVH_HANDOFF_WARPS=3),
+])
+def test_late_handoff_bit_exact(tor, oracle, env):
+    """BvhRenderParams::handoff: pixels parked at a sample boundary by lanes and by cooperative warps (generator state,
+    samples done, colour sum) and finished by the second launch of render_coop_kernel give the oracle's bits — the
+    knobs force the hand-off onto small renders, at sample 0 and in mid-flight."""
+    with _EnvCtx(tor, TOR_BVH_PREPASS_SPP=9, TOR_BVH_HANDOFF_ALL=1, TOR_BVH_DEAL_SORTED=2, **env) as ctx:
+        world, cam = tor.random_scene().list(), _book_cam(tor)
+        first = _check(tor, oracle, ctx, world, cam, 90, 160, 24)
+        # once more: the first launch of a kernel in a context loads its code, which shifts who sees the tail flag when
+        cv = tor.newCanvas(90, 160, 24, 2.2)
+        ctx.render(cv, cam, world, 50)
+        assert cv.pixels.tobytes() == first.pixels.tobytes()
+        parked = ctx.last_handoffs()
+        assert parked["from_lanes"] + parked["from_cooperative_warps"] > 0, parked
+        if env.get("TOR_BVH_COOP_FORCE") == 10 ** 9:
+            assert parked["from_cooperative_warps"] > 0, parked
+        _check(tor, oracle, ctx, world, cam, 54, 96, 12, rows=(5, 41, 7))
+        _check(tor, oracle, ctx, world, cam, 9, 11, 9)
+        for name, w in _handmade_scenes(tor).items():
+            _check(tor, oracle, ctx, w, cam, 30, 40, 10)
+        for depth in (0, 1, 2):
+            cv = tor.newCanvas(20, 30, 9, 2.2)
+            ctx.render(cv, cam, world, depth)
+            ref = oracle.render(20, 30, 9, cam.as_array(), world.objects, max_depth=depth, math="det")
+            assert cv.pixels.tobytes() == ref.tobytes()
 
 
 # ---------------------------------------------------------------------------------- device-resident animation

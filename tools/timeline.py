@@ -13,7 +13,8 @@ cv = T.newCanvas(675, 1200, 500, 2.2)
 for _ in range(2):
     ctx.render(cv, cam, world, 50, rows=(0, 675, step))
 print("kernel ms", ctx.last_kernel_ms(), ctx.last_schedule())
-coop, lanes = ctx.debug_times()
+coop, lanes, tail = ctx.debug_times()
+print('handoffs', ctx.last_handoffs())
 c = coop[coop[:, 1] > 0].astype(np.int64)
 l = lanes[lanes[:, 1] > 0].astype(np.int64)
 t0 = min(c[:, 0].min() if len(c) else 1 << 62, l[:, 0].min())
@@ -30,3 +31,13 @@ if len(c):
 late = np.argsort(-l[:, 1])[:5]
 for i in late:
     print("  late lane warp: start %.2f end %.2f" % ((l[i, 0] - t0) / 1e6, (l[i, 1] - t0) / 1e6))
+tl = tail[tail[:, 1] > 0].astype(np.int64)
+if len(tl):
+    d = (tl[:, 1] - tl[:, 0]) / 1e3
+    busy = tl[tl[:, 2] > 0]
+    print("hand-off warps", len(tl), "with work", len(busy), "start ms: min %.2f max %.2f" % ((tl[:, 0].min() - t0) / 1e6, (tl[:, 0].max() - t0) / 1e6),
+          "end ms: p50 %.2f p90 %.2f max %.2f" % tuple((np.percentile(busy[:, 1], q) - t0) / 1e6 for q in (50, 90, 100)) if len(busy) else "",
+          "segments: total %d max %d" % (tl[:, 2].sum(), tl[:, 2].max()))
+    for i in np.argsort(-tl[:, 1])[:5]:
+        print("  late hand-off warp: start %.2f end %.2f segs %d us/seg %.3f" % ((tl[i, 0] - t0) / 1e6, (tl[i, 1] - t0) / 1e6, tl[i, 2], (tl[i, 1] - tl[i, 0]) / 1e3 / max(1, tl[i, 2])))
+print("lane warp end histogram (ms):", np.histogram((l[:, 1] - t0) / 1e6, bins=12)[0].tolist(), "up to %.1f" % ((l[:, 1].max() - t0) / 1e6))

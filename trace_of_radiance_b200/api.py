@@ -57,7 +57,7 @@ EXPORTED_SYMBOLS = [
     "tor_launch_count", "tor_measure_fp64_peak", "tor_get_traversal_counters", "tor_scene_info", "tor_camera_make", "tor_random_scene", "tor_export_ppm", "tor_quantise_rgb8", "tor_animation_create",
     "tor_animation_next_frame", "tor_animation_destroy", "tor_render_rgb8", "tor_render_rgb8_async", "tor_host_alloc",
     "tor_host_free", "tor_render_ycbcr420", "tor_render_ycbcr420_async", "tor_h264_open", "tor_h264_frame_buffer",
-    "tor_h264_flush_frame", "tor_h264_finish", "tor_mp4_mux_h264_file", "tor_fast_substream_count", "tor_last_schedule", "tor_download_rows_async", "tor_animation_dev_create",
+    "tor_h264_flush_frame", "tor_h264_finish", "tor_mp4_mux_h264_file", "tor_fast_substream_count", "tor_last_schedule", "tor_last_handoffs", "tor_download_rows_async", "tor_animation_dev_create",
     "tor_animation_dev_next", "tor_animation_dev_sync", "tor_animation_dev_launch_count", "tor_animation_dev_destroy",
     "tor_animation_dev_reset", "tor_debug_times",
 ]
@@ -132,6 +132,7 @@ def load_library():
     L.tor_get_traversal_counters.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.tor_scene_info.argtypes = [vp, C.POINTER(C.c_int64)]
     L.tor_last_schedule.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.tor_last_handoffs.argtypes = [vp, C.POINTER(C.c_int64)]
     L.tor_debug_times.argtypes = [vp, vp, C.c_int64]
     L.tor_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.tor_launch_count.argtypes = [vp]
@@ -453,11 +454,19 @@ class Context:
         return {"cooperative_pixels": int(out[0]), "qualifying_pixels": int(out[1]), "prepass_segments": int(out[2]),
                 "devices": int(out[3])}
 
+    def last_handoffs(self):
+        """Pixels parked in the tail of the last cost-ranked render and finished by one warp each (tor_last_handoffs)."""
+        out = (C.c_int64 * 2)()
+        self._check(self.L.tor_last_handoffs(self.h, out))
+        return {"from_cooperative_warps": int(out[0]), "from_lanes": int(out[1])}
+
     def debug_times(self):
-        """(coop (4096, 3): start, end, segments; lanes (8192, 2): start, end) in ns (tor_debug_times)."""
-        out = np.zeros(3 * 4096 + 2 * 8192, dtype=np.uint64)
+        """(coop (4096, 3): start, end, segments; lanes (8192, 2): start, end; hand-off launch (4096, 3) like coop) in
+        ns (tor_debug_times)."""
+        out = np.zeros(3 * 4096 + 2 * 8192 + 3 * 4096, dtype=np.uint64)
         self._check(self.L.tor_debug_times(self.h, out.ctypes.data, out.size))
-        return out[:3 * 4096].reshape(4096, 3), out[3 * 4096:].reshape(8192, 2)
+        a, b = 3 * 4096, 3 * 4096 + 2 * 8192
+        return out[:a].reshape(4096, 3), out[a:b].reshape(8192, 2), out[b:].reshape(4096, 3)
 
     def last_kernel_ms(self):
         ms = C.c_float()

@@ -37,7 +37,7 @@ struct Tuning {
   bool queue_percost = false;  // TOR_BVH_EXACT_QUEUE=percost: one class per cost value, one atomic per lane
   bool no_scramble = false;    // TOR_BVH_NO_SCRAMBLE: row-major queue for renders without a cost pre-pass
   bool fast_scramble = false;  // TOR_BVH_FAST_SCRAMBLE: scattered queue in split-stream mode
-  float coop_alpha = 1.0f;     // TOR_BVH_COOP_ALPHA: a pixel is traced by a whole warp when its pre-pass cost
+  float coop_alpha = 0.7f;     // TOR_BVH_COOP_ALPHA: a pixel is traced by a whole warp when its pre-pass cost
                                //   exceeds alpha x the mean cost per lane of the launch
   int coop_max_pct = 15;       // TOR_BVH_COOP_MAX: at most this percentage of the SMs is set aside for cooperative
                                //   pixels, 8 per SM (0 switches the mechanism off)
@@ -45,6 +45,11 @@ struct Tuning {
                                //   cooperatively (tests), still capped by coop_max_pct
   int prepass_min_spp = 256;   // TOR_BVH_PREPASS_SPP: samples per pixel from which the cost pre-pass runs
   int coop_px_per_lane = 8;    // TOR_BVH_COOP_PXLANE: cooperative pixels only when the launch has fewer pixels per lane
+  int deal_sorted = 2;         // TOR_BVH_DEAL_SORTED: dealt wave by consecutive ranks per warp: 1 = launches with few pixels per lane, 2 = always
+  int handoff_pct = 75;        // TOR_BVH_HANDOFF: late hand-off once this % of the dealt lane warps are done (0 = off)
+  int handoff_min_left = 8;    // TOR_BVH_HANDOFF_MIN_LEFT: pixels with fewer samples left stay where they are
+  int handoff_warps = 16;      // TOR_BVH_HANDOFF_WARPS: working warps per CTA of the second cooperative launch
+  int handoff_all = 0;         // TOR_BVH_HANDOFF_ALL: also in launches without cooperative CTAs (many pixels per lane)
   int thin_px_per_lane = 0;    // TOR_BVH_THIN_PXLANE: launches with fewer pixels per lane than this / 100 run `thin_lanes`
   int thin_lanes = 16;         // TOR_BVH_THIN_LANES: lanes per warp of the dealt wave (0 = never)
   int coop_fast_pct = 0;       // TOR_BVH_COOP_FAST: this percentage of the cooperative CTAs runs only coop_fast_warps warps
@@ -96,6 +101,11 @@ struct Tuning {
     t.coop_warps = clampi(geti("TOR_BVH_COOP_WARPS", (int)tor::kCoopWarps), 1, 16);
     t.coop_fast_pct = clampi(geti("TOR_BVH_COOP_FAST", 0), 0, 100);
     t.coop_fast_warps = clampi(geti("TOR_BVH_COOP_FAST_WARPS", 8), 1, 16);
+    t.deal_sorted = clampi(geti("TOR_BVH_DEAL_SORTED", 2), 0, 2);
+    t.handoff_pct = clampi(geti("TOR_BVH_HANDOFF", 75), 0, 100);
+    t.handoff_min_left = clampi(geti("TOR_BVH_HANDOFF_MIN_LEFT", 8), 1, 1 << 20);
+    t.handoff_warps = clampi(geti("TOR_BVH_HANDOFF_WARPS", 16), 1, 16);
+    t.handoff_all = clampi(geti("TOR_BVH_HANDOFF_ALL", 0), 0, 1);
     t.thin_px_per_lane = clampi(geti("TOR_BVH_THIN_PXLANE", 0), 0, 100000);
     t.thin_lanes = clampi(geti("TOR_BVH_THIN_LANES", 16), 1, 32);
     t.stage_max = clampi(geti("TOR_BVH_STAGE", 2), 0, 2);
@@ -116,6 +126,8 @@ struct DeviceState {
   cudaStream_t stream_coop = nullptr;  // render_coop_kernel runs beside the lane kernel, at a higher priority
   cudaEvent_t ev_ranked = nullptr, ev_coop_done = nullptr;
   unsigned long long* d_dbg = nullptr;  // TOR_BVH_DEBUG_TIMES: %globaltimer stamps of the last exact-mode main launch
+  uint8_t* d_handoff = nullptr;      // parked pixels of the late hand-off (BvhRenderParams::handoff)
+  size_t handoff_cap = 0;
   unsigned int* d_ticket = nullptr;  // [0] arrival counter of the lane kernel's CTAs (BvhRenderParams::deal_ticket),
                                      // [1] cooperative CTAs resident (coop_gate_kernel)
   bool busy = false;
@@ -565,6 +577,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       // by the lanes.  Cooperative CTAs take whole SMs, so the grid must be the full persistent one.
       const bool few_pixels = total_px < lanes * (unsigned long long)tune.coop_px_per_lane;
       const bool full_grid = grid == per_sm * d.sm_count;
+      lay.sorted = (tune.deal_sorted == 2 || (tune.deal_sorted == 1 && few_pixels)) ? 1u : 0u;
       if (coherent && warps && tune.coop_max_pct > 0 && ((few_pixels && full_grid) || tune.coop_force >= 0)) {
         lay.coop_grid = std::max(1u, (uint32_t)((unsigned long long)d.sm_count * (unsigned)tune.coop_max_pct / 100ull));
         lay.n_fast = (uint32_t)((unsigned long long)lay.coop_grid * (unsigned)tune.coop_fast_pct / 100ull);
@@ -620,6 +633,22 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       P.coop_list = d.d_coop;
       P.coop = lay;
       P.deal_ticket = d.d_ticket;
+      if (tune.handoff_pct > 0 && coherent && warps && (lay.coop_grid > 0 || tune.handoff_all)) {
+        // late hand-off (BvhRenderParams::handoff): room for every cooperative pixel, one record per lane and the
+        // unassigned rest of every warp's last queue chunk (at most 32 slots)
+        const size_t need = ((size_t)coop_max + 2 * (size_t)lanes) * sizeof(tor::HandoffRec);
+        if (need > d.handoff_cap) {
+          if (d.d_handoff) cudaFree(d.d_handoff);
+          d.d_handoff = nullptr;
+          d.handoff_cap = 0;
+          TOR_CUDA(ctx, cudaMalloc(&d.d_handoff, need));
+          d.handoff_cap = need;
+        }
+        P.handoff = d.d_handoff;
+        P.handoff_cap_a = coop_max;
+        P.handoff_pct = (uint32_t)tune.handoff_pct;
+        P.handoff_min_left = (uint32_t)tune.handoff_min_left;
+      }
     } else if (reorder && sub_log2 == 0 && !tune.no_scramble) {
       // exact mode without cost information (few samples per pixel): scatter the image over the warps so that
       // expensive neighbours do not share one (BvhRenderParams::scramble).  Split-stream units are short, so there
@@ -629,13 +658,13 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
       P.scramble = coprime_near_golden((uint32_t)total_px);
     }
     if (tune.debug_times && !P.cost) {
-      const size_t bytes = (3 * 4096 + 2 * 8192) * sizeof(unsigned long long);
+      const size_t bytes = (3 * 4096 + 2 * 8192 + 3 * 4096) * sizeof(unsigned long long);
       if (!d.d_dbg) TOR_CUDA(ctx, cudaMalloc(&d.d_dbg, bytes));
       TOR_CUDA(ctx, cudaMemsetAsync(d.d_dbg, 0, bytes, stream));
       P.dbg_times = d.d_dbg;
     }
     const bool with_coop = P.sched != nullptr && P.coop.coop_grid > 0;
-    if (P.sched) TOR_CUDA(ctx, cudaMemsetAsync(d.d_ticket, 0, 4 * sizeof(unsigned int), stream));  // ticket, arrivals, queue head
+    if (P.sched) TOR_CUDA(ctx, cudaMemsetAsync(d.d_ticket, 0, 8 * sizeof(unsigned int), stream));  // BvhRenderParams::deal_ticket
     if (with_coop) {
       // render_coop_kernel on its own high-priority stream, launched first so that its CTAs take their SMs before the
       // lane kernel's grid fills the GPU; it reads the ranking the kernels above left on `stream`
@@ -651,6 +680,15 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     main_plan.fn<<<grid, block, main_plan.smem, stream>>>(P);
     TOR_CUDA(ctx, cudaGetLastError());
     if (with_coop) TOR_CUDA(ctx, cudaStreamWaitEvent(stream, d.ev_coop_done, 0));  // draw needs every pixel's sum
+    if (P.handoff) {
+      // the pixels that lanes and cooperative warps parked when the launch entered its tail: one warp each, all SMs
+      tor::BvhRenderParams H = P;
+      H.handoff_mode = 1;
+      H.coop.cw = (uint32_t)tune.handoff_warps;
+      tor::render_coop_kernel<<<d.sm_count, tor::kCoopBlock, 0, stream>>>(H);
+      TOR_CUDA(ctx, cudaGetLastError());
+      ctx->launches += 1;
+    }
     const unsigned long long nch = total_px * 3ull;
     if (sub_log2) {  // per-range partial sums -> pixel sums, fixed pairwise order
       const unsigned long long nthr = nch << sub_log2;
@@ -727,7 +765,7 @@ int tor_ctx_create(const int* devices, int ndev, tor_ctx** out) {
               cudaEventCreateWithFlags(&d.ev_ranked, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&d.ev_coop_done, cudaEventDisableTiming) == cudaSuccess &&
               create_priority_stream(&d.stream_coop) == cudaSuccess &&
-              cudaMalloc(&d.d_ticket, 4 * sizeof(unsigned int)) == cudaSuccess &&
+              cudaMalloc(&d.d_ticket, 8 * sizeof(unsigned int)) == cudaSuccess &&
               cudaMalloc(&d.d_work, 2 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&d.d_sched, 4 * sizeof(uint32_t)) == cudaSuccess &&
               cudaMemset(d.d_sched, 0, 4 * sizeof(uint32_t)) == cudaSuccess &&
@@ -760,6 +798,7 @@ void tor_ctx_destroy(tor_ctx* ctx) {
     if (d.ev_coop_done) cudaEventDestroy(d.ev_coop_done);
     if (d.stream_coop) cudaStreamDestroy(d.stream_coop);
     if (d.d_ticket) cudaFree(d.d_ticket);
+    if (d.d_handoff) cudaFree(d.d_handoff);
     if (d.d_dbg) cudaFree(d.d_dbg);
     if (d.d_pixels) cudaFree(d.d_pixels);
     if (d.d_work) cudaFree(d.d_work);
@@ -1061,11 +1100,27 @@ int tor_last_schedule(tor_ctx* ctx, int64_t out[4]) {
   return TOR_OK;
 }
 
+int tor_last_handoffs(tor_ctx* ctx, int64_t out[2]) {
+  if (!ctx || !out) return TOR_ERR_INVALID_ARG;
+  out[0] = out[1] = 0;
+  for (DeviceState& d : ctx->devs) {
+    unsigned int h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    TOR_CUDA(ctx, cudaSetDevice(d.dev));
+    TOR_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    int rc = wait_idle(ctx, d);
+    if (rc) return rc;
+    TOR_CUDA(ctx, cudaMemcpy(h, d.d_ticket, sizeof(h), cudaMemcpyDeviceToHost));
+    out[0] += h[5];
+    out[1] += h[6];
+  }
+  return TOR_OK;
+}
+
 int tor_debug_times(tor_ctx* ctx, uint64_t* out, int64_t n) {
   if (!ctx || !out) return TOR_ERR_INVALID_ARG;
   DeviceState& d = ctx->devs[0];
   if (!d.d_dbg) return fail(ctx, TOR_ERR_INVALID_ARG, "no stamps: create the context with TOR_BVH_DEBUG_TIMES set");
-  const int64_t have = 3 * 4096 + 2 * 8192;
+  const int64_t have = 3 * 4096 + 2 * 8192 + 3 * 4096;
   TOR_CUDA(ctx, cudaSetDevice(d.dev));
   TOR_CUDA(ctx, cudaDeviceSynchronize());
   TOR_CUDA(ctx, cudaMemcpy(out, d.d_dbg, (size_t)(n < have ? n : have) * sizeof(uint64_t), cudaMemcpyDeviceToHost));

@@ -49,6 +49,8 @@ struct CoopLayout {
   uint32_t per_sm;     // lane-kernel CTAs that one cooperative CTA keeps off its SM
   uint32_t lanes;      // lanes of each warp that take pixels (BvhRenderParams::lanes_per_warp): the dealt wave gives a
                        // warp `lanes` pixels; its slots in `order` stay 32 apart
+  uint32_t sorted;     // dealt wave: 0 = every warp gets the same mix of costs (tiers), 1 = every warp gets `lanes`
+                       // consecutive ranks and every CTA the same mix of warps (place_rank)
 };
 // cooperative CTAs that get pixels when K pixels are cooperative
 __host__ __device__ __forceinline__ uint32_t coop_ctas_used(const CoopLayout& c, uint32_t K) {
@@ -106,7 +108,8 @@ struct BvhRenderParams {
   CoopLayout coop;
   unsigned int* deal_ticket;
   // Developer aid (NULL in production): %globaltimer stamps — [3k..3k+2] = start, end, segments of cooperative warp k
-  // (k = CTA * kCoopWarps + warp) and, from entry 3 * 4096 on, [2w], [2w+1] = start and end of lane-kernel warp w.
+  // (k = CTA * kCoopWarps + warp), from entry 3 * 4096 on, [2w], [2w+1] = start and end of lane-kernel warp w, and
+  // from entry 3 * 4096 + 2 * 8192 on the warps of the hand-off launch like the cooperative ones.
   unsigned long long* dbg_times;
   // Lanes of each warp that take pixels (1..32; 32 unless the TOR_BVH_LANES tuning knob says otherwise).
   int32_t lanes_per_warp;
@@ -121,7 +124,29 @@ struct BvhRenderParams {
   uint32_t chunk;
   unsigned long long chunk_guard;
   uint32_t endgame_min_chunk;  // cost-ranked queue: smallest share a warp takes near the end (0: always `chunk`)
+  // Late hand-off (exact mode, cost-ranked launches; NULL = off).  Once `handoff_pct` % of the lane kernel's dealt
+  // warps have run out of work the launch is in its tail: the pixels still in flight are single serial chains on
+  // warps that are mostly idle.  From then on every lane — and every warp of the concurrent render_coop_kernel —
+  // parks its pixel at its next sample boundary as a HandoffRec {pixel, samples done, generator state, colour sum}
+  // and retires; a second launch of render_coop_kernel (handoff_mode = 1) on the whole GPU continues each parked
+  // pixel with one warp from exactly that state.  A pixel's stream and the order of its additions are untouched, so
+  // the image is the same bit for bit.  Records: [handoff_cap_a from cooperative warps — the longest chains, taken
+  // first][one per lane].  deal_ticket[3] = dealt lane warps that are done, [4] = the tail flag, [5], [6] = records
+  // in the two regions, [7] = queue head of the second launch.
+  uint8_t* handoff;
+  uint32_t handoff_cap_a;
+  uint32_t handoff_pct;
+  uint32_t handoff_min_left;  // a pixel with fewer samples left than this stays where it is
+  uint32_t handoff_mode;
 };
+
+struct __align__(16) HandoffRec {
+  uint32_t pid;
+  int32_t sample;  // samples already in the sum (Lane::sample)
+  uint64_t s0, s1, s2, s3;
+  double px, py, pz;
+};
+static_assert(sizeof(HandoffRec) == 64, "HandoffRec is one 64-byte record");
 
 // One object of a leaf (or of the "always" list) against the ray: the reference's arithmetic
 // (spheres.nim:28-49 / moving_spheres.nim:39-67), operation for operation.  r2 = radius*radius and
@@ -326,14 +351,22 @@ __device__ __forceinline__ bool slab_test(const SlabRay& R, float best_f, float 
 // Launched beside the lane kernel on its own high-priority stream (tor_api.cu); see CoopLayout for the placement.
 __global__ void __launch_bounds__(kCoopBlock, 1) render_coop_kernel(const __grid_constant__ BvhRenderParams P) {
   const uint32_t warp = threadIdx.x >> 5;
-  const bool fast_cta = blockIdx.x < P.coop.n_fast;
+  const bool resume = P.handoff_mode != 0;  // second launch: continue the parked pixels (BvhRenderParams::handoff)
+  const bool fast_cta = !resume && blockIdx.x < P.coop.n_fast;
   if (warp >= (fast_cta ? P.coop.cw_fast : P.coop.cw)) return;  // the other warps only hold the SM's registers
-  const uint32_t n_coop = P.sched[0];
-  const uint32_t n_used = coop_ctas_used(P.coop, n_coop);
-  if (blockIdx.x >= n_used) return;
+  const uint32_t n_coop = resume ? 0u : P.sched[0];
+  if (!resume && blockIdx.x >= coop_ctas_used(P.coop, n_coop)) return;
   // first pixel of a fast CTA's warp: fixed (the head of the ranking, spread over the fast CTAs)
   uint32_t first_px = fast_cta ? warp * P.coop.n_fast + blockIdx.x : 0xffffffffu;
-  if (threadIdx.x == 0) atomicAdd(P.deal_ticket + 1, 1u);  // resident: coop_gate_kernel lets the lane kernel start
+  if (!resume && threadIdx.x == 0) atomicAdd(P.deal_ticket + 1, 1u);  // resident: coop_gate_kernel lets the lane kernel start
+  // parked pixels: region A first; the first gridDim.x * cw records go out round-robin over the CTAs (the longest
+  // chains end up on different SMs), the rest through deal_ticket[7]
+  const uint32_t n_rec_a = resume ? P.deal_ticket[5] : 0u, n_rec = resume ? n_rec_a + P.deal_ticket[6] : 0u;
+  uint32_t first_rec = resume ? warp * gridDim.x + blockIdx.x : 0xffffffffu;
+  HandoffRec* const rec_a = reinterpret_cast<HandoffRec*>(P.handoff);
+  HandoffRec* const rec_b = rec_a + P.handoff_cap_a;
+  const bool may_park = !resume && P.handoff != nullptr;
+  uint32_t tail_seen = 0;  // lane 0: the tail flag as of the previous sample (the load is consumed a sample later)
   unsigned long long dbg_t0 = 0;
   if (P.dbg_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
   const BvhView& bv = P.bv;
@@ -360,25 +393,71 @@ __global__ void __launch_bounds__(kCoopBlock, 1) render_coop_kernel(const __grid
   // The cooperative pixels are a queue, most expensive first: a warp that finishes one takes the next, so the SMs
   // that are set aside stay busy until the list is empty (there may be several times more pixels than warps).
   for (;;) {
-    uint32_t cr = first_px;
-    first_px = 0xffffffffu;
-    if (cr == 0xffffffffu) {  // the shared queue starts behind the fast CTAs' first pixels
-      if (lane == 0) cr = P.coop.n_fast * P.coop.cw_fast + atomicAdd(P.deal_ticket + 2, 1u);
-      cr = __shfl_sync(0xffffffffu, cr, 0);
+    uint32_t pid;
+    int32_t s_first = 0;
+    if (resume) {
+      uint32_t k = first_rec;
+      first_rec = 0xffffffffu;
+      if (k == 0xffffffffu) {
+        if (lane == 0) k = gridDim.x * P.coop.cw + atomicAdd(P.deal_ticket + 7, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+      }
+      if (k >= n_rec) break;
+      const HandoffRec h = k < n_rec_a ? rec_a[k] : rec_b[k - n_rec_a];
+      pid = h.pid;
+      s_first = h.sample;
+      L.rng.s0 = h.s0;
+      L.rng.s1 = h.s1;
+      L.rng.s2 = h.s2;
+      L.rng.s3 = h.s3;
+      L.pix = v3(h.px, h.py, h.pz);
+    } else {
+      uint32_t cr = first_px;
+      first_px = 0xffffffffu;
+      if (cr == 0xffffffffu) {  // the shared queue starts behind the fast CTAs' first pixels
+        if (lane == 0) cr = P.coop.n_fast * P.coop.cw_fast + atomicAdd(P.deal_ticket + 2, 1u);
+        cr = __shfl_sync(0xffffffffu, cr, 0);
+      }
+      if (cr >= n_coop) {
+        if (cr < P.coop.n_fast * P.coop.cw_fast) continue;  // a fast warp without a first pixel: on to the queue
+        break;
+      }
+      pid = P.coop_list[cr];
     }
-    if (cr >= n_coop) {
-      if (cr < P.coop.n_fast * P.coop.cw_fast) continue;  // a fast warp without a first pixel: on to the queue
-      break;
-    }
-    const uint32_t pid = P.coop_list[cr];
     {
       const int32_t ri = (int32_t)(pid / (uint32_t)P.ncols);
       L.col = (int32_t)(pid - (uint32_t)ri * (uint32_t)P.ncols);
       L.row = P.row_begin + ri * P.row_step;
     }
-    rng_seed_pixel(L.rng, L.row, L.col, 0);  // render.nim:59-60
-    L.pix = v3(0, 0, 0);
-    for (int32_t s = 0; s < P.spp; ++s) {  // render.nim:62
+    if (!resume) {
+      rng_seed_pixel(L.rng, L.row, L.col, 0);  // render.nim:59-60
+      L.pix = v3(0, 0, 0);
+    }
+    bool parked = false;
+    for (int32_t s = s_first; s < P.spp; ++s) {  // render.nim:62
+      if (may_park) {
+        // the launch is in its tail: park the pixel (also one not yet started) for the second launch, which spreads
+        // what is left over every SM
+        const uint32_t tail = __shfl_sync(0xffffffffu, tail_seen, 0);
+        if (tail && P.spp - s >= (int32_t)P.handoff_min_left) {
+          if (lane == 0) {
+            HandoffRec h;
+            h.pid = pid;
+            h.sample = s;
+            h.s0 = L.rng.s0;
+            h.s1 = L.rng.s1;
+            h.s2 = L.rng.s2;
+            h.s3 = L.rng.s3;
+            h.px = L.pix.x;
+            h.py = L.pix.y;
+            h.pz = L.pix.z;
+            rec_a[atomicAdd(P.deal_ticket + 5, 1u)] = h;
+          }
+          parked = true;
+          break;
+        }
+        if (lane == 0) tail_seen = *(volatile const unsigned int*)(P.deal_ticket + 4);
+      }
       start_sample(L, P.cam, P.nrows, P.ncols);
       if (lane == 0) ++ray_count;
       V3 color = v3(0, 0, 0);
@@ -493,7 +572,7 @@ __global__ void __launch_bounds__(kCoopBlock, 1) render_coop_kernel(const __grid
       L.pix.y += color.y;
       L.pix.z += color.z;
     }
-    if (lane == 0) {
+    if (lane == 0 && !parked) {
       double* out = P.pixels + 3ull * pid;  // the sum; draw_kernel applies canvas.nim:47-54 afterwards
       out[0] = L.pix.x;
       out[1] = L.pix.y;
@@ -504,7 +583,7 @@ __global__ void __launch_bounds__(kCoopBlock, 1) render_coop_kernel(const __grid
   if (P.dbg_times && lane == 0) {
     unsigned long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    unsigned long long* e = P.dbg_times + 3ull * (blockIdx.x * P.coop.cw + warp);
+    unsigned long long* e = P.dbg_times + (resume ? 3ull * 4096ull + 2ull * 8192ull : 0ull) + 3ull * (blockIdx.x * P.coop.cw + warp);
     e[0] = dbg_t0;
     e[1] = t1;
     e[2] = seg_count;
@@ -614,6 +693,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
   bool first_fetch = P.first_wave != 0 && deal_rank != 0xffffffffu;  // warps that are dealt nothing go straight to the queue
   bool trav_done = false;  // the current segment's closest hit is final
   bool need_setup = false;  // a new segment needs its traversal state
+  bool tail_on = false;     // late hand-off: the launch is in its tail (warp-uniform)
+  unsigned int tail_seen = 0;
   unsigned long long seg_count = 0, ray_count = 0;
   uint32_t box_count = 0, test_count = 0;  // per lane: far below 2^32 (a lane sees ~1e5 segments per render)
 
@@ -801,6 +882,56 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
         }
       }
     }
+    if (P.handoff) {
+      // Late hand-off (BvhRenderParams::handoff).  Every warp watches the tail flag (lane 0 loads it, the value is
+      // used one pass later so that nobody waits for the load); once it is up every lane parks its pixel at its next
+      // sample boundary.
+      if (!tail_on) {
+        tail_on = __shfl_sync(0xffffffffu, tail_seen, 0) != 0;
+        if ((tid & 31) == 0) tail_seen = *(volatile const unsigned int*)(P.deal_ticket + 4);
+      }
+      if (tail_on && active && need_sample && P.spp - L.sample >= (int32_t)P.handoff_min_left) {
+        HandoffRec h;
+        h.pid = pid;
+        h.sample = L.sample;
+        h.s0 = L.rng.s0;
+        h.s1 = L.rng.s1;
+        h.s2 = L.rng.s2;
+        h.s3 = L.rng.s3;
+        h.px = L.pix.x;
+        h.py = L.pix.y;
+        h.pz = L.pix.z;
+        reinterpret_cast<HandoffRec*>(P.handoff)[P.handoff_cap_a + atomicAdd(P.deal_ticket + 6, 1u)] = h;
+        active = false;
+        need_sample = false;
+      }
+      if constexpr (CHUNKED) {
+        // The queue slots this warp took as a chunk but has not handed to a lane yet would otherwise be lost when the
+        // warp retires: park them as pixels that have not started.
+        while (tail_on) {
+          const unsigned long long next = wchunk[0], end = wchunk[1];
+          if (next >= end) break;
+          const unsigned long long slot = next + (unsigned long long)(tid & 31);
+          __syncwarp();
+          if ((tid & 31) == 0) wchunk[0] = next + 32ull < end ? next + 32ull : end;
+          __syncwarp();
+          if (slot < end) {
+            HandoffRec h;
+            h.pid = P.order ? P.order[first_wave + slot] : unit_of_slot(slot);
+            const int32_t ri = (int32_t)(h.pid / (uint32_t)P.ncols);
+            Rng g;
+            rng_seed_pixel(g, P.row_begin + ri * P.row_step, (int32_t)(h.pid - (uint32_t)ri * (uint32_t)P.ncols), 0);
+            h.sample = 0;
+            h.s0 = g.s0;
+            h.s1 = g.s1;
+            h.s2 = g.s2;
+            h.s3 = g.s3;
+            h.px = h.py = h.pz = 0.0;
+            reinterpret_cast<HandoffRec*>(P.handoff)[P.handoff_cap_a + atomicAdd(P.deal_ticket + 6, 1u)] = h;
+          }
+        }
+      }
+    }
     if (!__any_sync(0xffffffffu, active)) break;
 
     if (active && need_sample) {
@@ -905,6 +1036,12 @@ __global__ void __launch_bounds__(BLOCK, BLOCK <= 256 ? 512 / BLOCK : 1) render_
     __syncwarp();
   }
 
+  if (P.handoff && (tid & 31) == 0 && deal_rank != 0xffffffffu) {
+    // this dealt warp is done: raise the tail flag once handoff_pct % of them are
+    const unsigned int done = atomicAdd(P.deal_ticket + 3, 1u) + 1u;
+    if ((unsigned long long)done * 100ull >= (unsigned long long)P.handoff_pct * (unsigned long long)n_deal_warps)
+      *(volatile unsigned int*)(P.deal_ticket + 4) = 1u;
+  }
   if (P.dbg_times && (tid & 31) == 0) {
     unsigned long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -1035,7 +1172,7 @@ __global__ void __launch_bounds__(kCostBuckets) cost_offsets_kernel(uint32_t* __
 // in neighbouring lanes of the same tier, and the ranks after the first wave are queued in order.
 // warps_all = warps of the render grid (0: no dealing, everything is queued).
 struct RankLayout {
-  uint32_t n_coop, warps, first_wave, tier, n_first;
+  uint32_t n_coop, warps, first_wave, tier, n_first, lanes, wpc, sorted;
 };
 __device__ __forceinline__ RankLayout rank_layout(const uint32_t* __restrict__ sched, uint32_t n, uint32_t warps_all,
                                                   uint32_t group, const CoopLayout& coop) {
@@ -1045,7 +1182,10 @@ __device__ __forceinline__ RankLayout rank_layout(const uint32_t* __restrict__ s
   r.first_wave = r.warps * 32u;
   r.tier = r.warps * group;
   const uint32_t n_ranked = n - r.n_coop;
-  const uint32_t cap = r.warps * (coop.lanes ? coop.lanes : 32u);  // tiers fill lanes 0 .. lanes-1 of every warp
+  r.lanes = coop.lanes ? coop.lanes : 32u;
+  r.wpc = coop.wpc ? coop.wpc : 1u;
+  r.sorted = (coop.sorted && r.warps >= r.wpc && r.warps % r.wpc == 0) ? 1u : 0u;
+  const uint32_t cap = r.warps * r.lanes;  // the dealt wave fills lanes 0 .. lanes-1 of every warp
   r.n_first = n_ranked < cap ? n_ranked : cap;
   return r;
 }
@@ -1057,7 +1197,13 @@ __device__ __forceinline__ void place_rank(const RankLayout& r, uint32_t pos, ui
   }
   pos -= r.n_coop;
   uint32_t slot;
-  if (pos < r.n_first) {
+  if (pos < r.n_first && r.sorted) {
+    // warp w of the ranking = `lanes` consecutive ranks; dealing rank = ticket of the CTA * wpc + warp inside the CTA
+    // (render_bvh_kernel), so w -> CTA w mod ctas, warp w / ctas: equally expensive warps sit in different CTAs
+    const uint32_t w = pos / r.lanes, l = pos - w * r.lanes;
+    const uint32_t ctas = r.warps / r.wpc;
+    slot = ((w % ctas) * r.wpc + w / ctas) * 32u + l;
+  } else if (pos < r.n_first) {
     const uint32_t t = pos / r.tier, q = pos - t * r.tier;
     slot = (q % r.warps) * 32u + t * group + q / r.warps;
   } else {
