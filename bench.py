@@ -325,6 +325,8 @@ def _run_ours_on_stream(args, wl, rank, world_size, local_rank, dev, torch, dist
     clocks = sampler.stop() if sampler else None
     launches = ctx.launch_count() - launches0
     sched = ctx.last_schedule() if args.mode == "exact" and args.route == "bvh" else None
+    if sched is not None:
+        sched["parked_in_tail"] = ctx.last_handoffs()  # rank 0's launch: pixels finished by the hand-off launch
     if dev_ms < 0.98 * kern_ms:
         raise SystemExit(f"timing events ({dev_ms:.3f} ms) do not bracket the render kernel ({kern_ms:.3f} ms)")
     rays_per_step = nrows * ncols * spp

@@ -1,6 +1,6 @@
 #!/bin/bash
 # N-GPU bench lines the way the driver launches them (+ the in-process multi-device test)
-# usage: tools/gpu_multi.sh N TAG [c5]
+# usage: tools/gpu_multi.sh N TAG [c5|c2only]
 N=${1:-2}
 TAG=${2:-r02}
 mkdir -p gpurun_out
@@ -20,5 +20,5 @@ PY
   tail -2 gpurun_out/${TAG}_bench_$1_n$N.err | cut -c1-300
 }
 run c2 29511 --steps 5 --warmup 3
-run c4 29513 --steps 2 --warmup 1
+if [ "$3" != "c2only" ]; then run c4 29513 --steps 2 --warmup 1; fi
 if [ "$3" = "c5" ]; then run c5 29515 --steps 1 --warmup 1; fi

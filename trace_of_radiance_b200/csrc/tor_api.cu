@@ -501,7 +501,7 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     // Pixel scheduling.  A pixel's samples are a serial chain, so the order in which pixels start
     // decides when the render ends.  With enough samples per pixel a cost pre-pass (the first `pre` samples of every
     // pixel, only their segment counts kept) ranks the pixels; the few most expensive ones are traced by a whole warp
-    // each, the next ones are dealt to the lanes so that every warp starts with the same mix of costs, the rest is
+    // each, the next ones are dealt to the lanes (32 consecutive ranks per warp, every SM the same mix of warps), the rest is
     // queued most-expensive-first.
     const unsigned long long lanes = (unsigned long long)grid * block;
     // Split-stream queue: a warp takes 64 consecutive units at a time when every lane gets plenty of them, 32 (one

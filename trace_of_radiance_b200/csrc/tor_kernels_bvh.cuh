@@ -93,8 +93,8 @@ struct BvhRenderParams {
   uint32_t scramble;
   // order != NULL and first_wave != 0: the head of `order` is not queued but dealt, 32 entries per warp: lane l of
   // the warp with dealing rank w starts on order[32 * w + l] (0xffffffff = nothing), and the queue serves what
-  // follows.  The host deals the most expensive pixels so that every warp starts with the same mix of costs
-  // (cost_scatter_ordered_kernel).  first_wave = 32 * (warps of the grid): the dealt region when no warp is
+  // follows.  The scatter kernels deal the most expensive pixels: consecutive ranks per warp (CoopLayout::sorted)
+  // or tiers (place_rank).  first_wave = 32 * (warps of the grid): the dealt region when no warp is
   // cooperative; with n_coop cooperative warps (below) the region is 32 * (warps - n_coop) entries and the queue
   // starts right behind it.  Both the scatter kernels and this kernel derive the layout from sched[0].
   uint32_t first_wave;
@@ -1166,10 +1166,12 @@ __global__ void __launch_bounds__(kCostBuckets) cost_offsets_kernel(uint32_t* __
 }
 
 // pos = rank of the pixel, most expensive first.  Ranks below n_coop = sched[0] go to the cooperative warps
-// (coop_list[pos]).  The next ranks are dealt to the remaining warps' lanes like cards, in tiers of `group` lanes:
-// ranks 0 .. warps*group-1 go to lanes 0..group-1 of the warps (rank q -> warp q mod warps), the next warps*group ranks
-// to lanes group..2*group-1, and so on.  Every warp starts with the same mix of costs, equally expensive pixels sit
-// in neighbouring lanes of the same tier, and the ranks after the first wave are queued in order.
+// (coop_list[pos]).  The next ranks are dealt to the remaining warps' lanes, one pixel per lane.  Default
+// (CoopLayout::sorted): warp w of the ranking gets the consecutive ranks 32w .. 32w+31 — equally expensive pixels,
+// neighbours in the image inside a cost class, so its lanes finish together — and sits in CTA w mod CTAs, so every SM
+// holds the same mix of warps.  Otherwise like cards, in tiers of `group` lanes: ranks 0 .. warps*group-1 go to lanes
+// 0..group-1 of the warps (rank q -> warp q mod warps), the next warps*group ranks to lanes group..2*group-1, and so
+// on: every warp starts with the same mix of costs.  The ranks after the first wave are queued in order.
 // warps_all = warps of the render grid (0: no dealing, everything is queued).
 struct RankLayout {
   uint32_t n_coop, warps, first_wave, tier, n_first, lanes, wpc, sorted;
