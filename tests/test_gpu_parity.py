@@ -43,6 +43,7 @@ def test_small_random_scene_bit_exact(tor, oracle, gpu_ctx):
 def test_c1_bit_exact_and_equals_reference_png(tor, oracle, gpu_ctx):
     """Config C1 = trace_of_radiance.nim:27-57 (384x216, 100 spp, depth 50, gamma 2.2)."""
     cv = _check(tor, oracle, gpu_ctx, tor.random_scene().list(), _book_cam(tor), 216, 384, 100)
+    assert gpu_ctx.last_handoffs()["from_lanes"] > 0  # about one pixel per lane: the tail goes to one warp per pixel
     digest = json.load(open(os.path.join(GOLD, "c1_oracle_digest.json")))
     assert hashlib.sha256(cv.pixels.tobytes()).hexdigest() == digest["det"]["f64_sha256"]
     png = np.load(os.path.join(GOLD, "book2_motion_blur_rgb8.npz"))["rgb8"]
