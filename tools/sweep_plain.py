@@ -1,5 +1,6 @@
-"""Developer tool: renders without a cost pre-pass (100 spp) at several canvas sizes, with and without the late hand-off
-(TOR_BVH_HANDOFF_PLAIN); images compared with each other bit for bit."""
+"""Developer tool: renders with few samples per pixel at several canvas sizes: scrambled queue, the same with the late
+hand-off (TOR_BVH_HANDOFF_PLAIN), the cost-ranked path forced on, and the default policy; images compared with each
+other bit for bit."""
 import os
 import sys
 
@@ -11,10 +12,10 @@ from sweep_env import ctx_with  # noqa: E402
 
 world = T.random_scene(0xFACADE, 11).list()
 cam = T.camera((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 16.0 / 9.0, 0.1, 10.0, 0.0, 1.0)
-sizes = [(144, 256, 100), (216, 384, 100), (216, 384, 32), (270, 480, 100), (360, 640, 100), (450, 800, 100), (540, 960, 100), (675, 1200, 100), (1080, 1920, 100), (675, 1200, 255)]
-ctxs = {name: ctx_with(dict(env, TOR_BVH_HANDOFF_PLAIN_PXLANE=64)) for name, env in (
-    ("off", {"TOR_BVH_HANDOFF_PLAIN": 0}), ("p20", {"TOR_BVH_HANDOFF_PLAIN": 20}), ("p30", {"TOR_BVH_HANDOFF_PLAIN": 30}),
-    ("p40", {"TOR_BVH_HANDOFF_PLAIN": 40}), ("p70", {"TOR_BVH_HANDOFF_PLAIN": 70}))}
+sizes = [(144, 256, 100), (216, 384, 100), (216, 384, 32), (216, 384, 64), (675, 1200, 32), (675, 1200, 64), (270, 480, 100), (360, 640, 100), (450, 800, 100), (540, 960, 100), (675, 1200, 100), (1080, 1920, 100), (675, 1200, 255)]
+ctxs = {name: ctx_with(env) for name, env in (
+    ("plain", {"TOR_BVH_HANDOFF_PLAIN": 0, "TOR_BVH_PREPASS_FULL_SPP": 100000}),
+    ("plain+handoff", {"TOR_BVH_PREPASS_FULL_SPP": 100000}), ("ranked", {"TOR_BVH_PREPASS_SPP": 16}), ("default", {}))}
 for h, w, spp in sizes:
     ref, line = None, []
     for name, ctx in ctxs.items():

@@ -43,7 +43,8 @@ struct Tuning {
                                //   pixels, 8 per SM (0 switches the mechanism off)
   long long coop_force = -1;   // TOR_BVH_COOP_FORCE: trace exactly this many of the most expensive pixels
                                //   cooperatively (tests), still capped by coop_max_pct
-  int prepass_min_spp = 256;   // TOR_BVH_PREPASS_SPP: samples per pixel from which the cost pre-pass runs
+  int prepass_min_spp = 256;   // TOR_BVH_PREPASS_SPP: samples per pixel from which the cost pre-pass always runs
+  int prepass_full_spp = 64;   // TOR_BVH_PREPASS_FULL_SPP: ... and from which it runs when the launch fills the GPU
   int coop_px_per_lane = 8;    // TOR_BVH_COOP_PXLANE: cooperative pixels only when the launch has fewer pixels per lane
   int deal_sorted = 2;         // TOR_BVH_DEAL_SORTED: dealt wave by consecutive ranks per warp: 1 = launches with few pixels per lane, 2 = always
   int handoff_pct = 75;        // TOR_BVH_HANDOFF: late hand-off once this % of the dealt lane warps are done (0 = off)
@@ -97,6 +98,7 @@ struct Tuning {
     t.coop_max_pct = clampi(geti("TOR_BVH_COOP_MAX", 15), 0, 50);
     if (const char* e = getenv("TOR_BVH_COOP_FORCE")) t.coop_force = atoll(e);
     t.prepass_min_spp = clampi(geti("TOR_BVH_PREPASS_SPP", 256), 9, 1 << 30);
+    t.prepass_full_spp = clampi(geti("TOR_BVH_PREPASS_FULL_SPP", 64), 9, 1 << 30);
     t.coop_px_per_lane = clampi(geti("TOR_BVH_COOP_PXLANE", 8), 0, 1 << 20);
     t.coop_queue_factor = clampi(geti("TOR_BVH_COOP_QUEUE", 4), 1, 64);
     t.endgame_min_chunk = clampi(geti("TOR_BVH_ENDGAME", 4), 0, 32);
@@ -517,7 +519,13 @@ int launch_rows(tor_ctx* ctx, DeviceState& d, double* d_out, int32_t nrows, int3
     if (P.chunk == 0) P.chunk = (total_px << sub_log2) >= lanes * 64ull ? 64u : 32u;
     // below 256 spp the pre-pass costs more than the order gains (C1: +1 ms); split-stream units are short and
     // plentiful, so they need no ranking either
-    const int32_t pre = (spp >= tune.prepass_min_spp && sub_log2 == 0) ? 8 : 0;
+    // From 64 spp the ranking pays when the launch has the whole GPU (1200x675: -10 % at 64 spp, -16 % at 100, -21 % at
+    // 255; C1: 10.4 -> 9.0 ms) — the queue it builds keeps neighbouring, equally expensive pixels in one warp.  Not for
+    // canvases that leave SMs empty (256x144: the hand-off needs the cooperative path's full grid) and not for the
+    // animation's frames in flight (C4: 0.97 -> 1.11 s).
+    const bool owns_gpu = (unsigned long long)grid == cap && ctx->grid_divisor <= 1;
+    const int32_t pre =
+        (sub_log2 == 0 && (spp >= tune.prepass_min_spp || (owns_gpu && spp >= tune.prepass_full_spp))) ? 8 : 0;
     if (sub_log2) {
       const size_t need = (size_t)(total_px << sub_log2) * 3 * sizeof(double);
       if (need > d.partial_cap) {
