@@ -436,6 +436,10 @@ def test_late_handoff_bit_exact(tor, oracle, env):
         _check(tor, oracle, ctx, world, cam, 9, 11, 9)
         for name, w in _handmade_scenes(tor).items():
             _check(tor, oracle, ctx, w, cam, 30, 40, 10)
+        an = oracle.Animation(height=36, width=64, t_max=9.0)  # 1 601 movers with their own shutter interval
+        cam_arr, objs = an.next_frame(skip=6)
+        _check(tor, oracle, ctx, tor.HittableList(objs), tor.Camera.from_array(cam_arr), 36, 64, 9)
+        _check(tor, oracle, ctx, tor.random_scene(0xFACADE, 50).list(), cam, 18, 32, 9)  # 10 002 spheres, nothing staged
         for depth in (0, 1, 2):
             cv = tor.newCanvas(20, 30, 9, 2.2)
             ctx.render(cv, cam, world, depth)
