@@ -17,6 +17,9 @@ animation c4: all 300 frames, frame f on rank f mod N, + one gather of the RGB8 
             roofline.hbm — it is ~1e-5 by construction (a megakernel writes the framebuffer once).
 `image_check`: sha256 of the image that arrived on rank 0 against the CPU oracle's digest of the full frame
             (tests/golden/c2_oracle_digest.json) — at every GPU count the same bits.
+`schedule`: what the device-side pixel scheduling of rank 0's last launch did: pixels traced by
+            a whole warp, pixels whose pre-pass cost qualified, pixels parked in the launch's tail and finished by the
+            hand-off launch.  Scheduling cannot change the image.
 `cpu_baseline`: the oracle (C++ restatement of the reference, glibc libm, OpenMP over all host cores) timed on
             a bounded row sample of the same workload.  The Nim/Weave binary cannot be built (no nim).
 """
